@@ -1,0 +1,629 @@
+// flashmoe_b200.cu -- host runtime + C-ABI (include/flashmoe_b200.h) around the fused sm_100a kernel.
+//
+// Replaces the used slice of the reference's host runtime: bootstrap.cuh:278-512 (symmetric heap + bookkeeping
+// allocation, peer pointer tables), moe.cuh:146-205 (launch) and python_bindings.cu:17-151 (argument checks) --
+// without NVSHMEM (peer mapping is CUDA IPC or caller-provided pointers), without per-call weight copies
+// (python_bindings.cu:76-120 re-uploads every weight on every call) and without exit() on errors.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fm_kernel.cuh"
+
+// ---- compile-time configuration surface: csrc/flashmoe_config.json -> -DFM_CFG_* (build script) -------------
+#ifndef FM_CFG_CAPACITY_FACTOR
+#define FM_CFG_CAPACITY_FACTOR 1
+#define FM_CFG_DROP_TOKENS 1
+#define FM_CFG_EXPERT_TOP_K 2
+#define FM_CFG_GLOBAL_BATCH 256
+#define FM_CFG_IS_TRAINING 0
+#define FM_CFG_HIDDEN_ACT 0
+#define FM_CFG_HIDDEN_SIZE 1024
+#define FM_CFG_INTERMEDIATE_SIZE 4096
+#define FM_CFG_MINI_BATCH 1
+#define FM_CFG_MOE_FREQUENCY 1
+#define FM_CFG_NUM_EXPERTS 8
+#define FM_CFG_NUM_LAYERS 1
+#define FM_CFG_SEQUENCE_LEN 4096
+#define FM_CFG_TORCH_DTYPE 2
+#define FM_CFG_VOCAB_SIZE 32000
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define FM_CUDA(expr)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(FM_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D row-major bf16 tensor [rows, cols], tile box [box_rows, 64 cols], 128-byte swizzle (matches the UMMA smem
+// descriptors built in fm_ptx.cuh), out-of-bounds elements read as zero.
+int make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) return fail(FM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)fm::BLOCK_K, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(FM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (base=%p rows=%llu cols=%llu)", (int)r,
+                    base, (unsigned long long)rows, (unsigned long long)cols);
+    return FM_OK;
+}
+
+}  // namespace
+
+struct fm_ctx {
+    fm_config_t cfg;
+    fm_dims_t d;
+    int device = 0;
+    int grid = 0;
+    int tpc = 0;
+    int TN0 = 0, TN1 = 0, num_pkts = 0, num_blocks = 0, total_items = 0;
+    uint32_t epoch = 0;
+    unsigned long long bar_count = 0;
+    unsigned long long timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+    uint64_t launches = 0;
+    // device buffers
+    int* topk_idx = nullptr;
+    __nv_bfloat16* topk_w = nullptr;
+    float* mcw = nullptr;
+    int* slot = nullptr;
+    int* counts = nullptr;
+    __nv_bfloat16* gate_out = nullptr;
+    int* chunk_counts = nullptr;
+    unsigned int* ctrl = nullptr;  // [0] disp_done, [1] claim, [2..3] grid barrier (u64)
+    unsigned int* g0_done = nullptr;
+    unsigned int* g1_done = nullptr;
+    int* recv_cnt = nullptr;
+    fm::TileBlock* blocks = nullptr;
+    __nv_bfloat16* hidden = nullptr;
+    __nv_bfloat16* x_stage = nullptr;    // host-path staging
+    __nv_bfloat16* out_stage = nullptr;
+    // symmetric slab
+    void* symm = nullptr;
+    bool symm_external = false;
+    size_t symm_bytes = 0, off_recv_x = 0, off_ret_y = 0, off_recv_flag = 0, off_ret_flag = 0;
+    void* peer_base[FM_MAX_WORLD] = {};
+    bool peer_opened[FM_MAX_WORLD] = {};
+    bool attached = false;
+    fm::DebugRecord* dbg_host = nullptr;
+    fm::DebugRecord* dbg_dev = nullptr;
+    // tensor-map cache (re-encoded only when the caller's weight pointer changes)
+    const void* cached_expert_w = nullptr;
+    CUtensorMap tm_a0, tm_b0, tm_a1, tm_b1;
+    bool tm_static_ready = false;
+};
+
+namespace {
+
+int validate_config(const fm_config_t& c, int world, fm_dims_t* d) {
+    if (c.torch_dtype != 2) return fail(FM_EINVAL, "torch_dtype=%d: this build computes in bf16 only (2)", c.torch_dtype);
+    if (c.is_training != 0) return fail(FM_EINVAL, "is_training=1 is not implemented (forward-only build)");
+    if (c.hidden_act != 0 && c.hidden_act != 1) return fail(FM_EINVAL, "hidden_act must be 0 (relu) or 1 (gelu)");
+    if (c.drop_tokens != 0 && c.drop_tokens != 1) return fail(FM_EINVAL, "drop_tokens must be 0 or 1");
+    if (c.capacity_factor < 1) return fail(FM_EINVAL, "capacity_factor must be >= 1");
+    if (c.hidden_size <= 0 || c.hidden_size % 64) return fail(FM_EINVAL, "hidden_size must be a positive multiple of 64");
+    if (c.intermediate_size <= 0 || c.intermediate_size % 64)
+        return fail(FM_EINVAL, "intermediate_size must be a positive multiple of 64");
+    if (c.mini_batch < 1 || c.sequence_len < 1) return fail(FM_EINVAL, "mini_batch and sequence_len must be >= 1");
+    const long long S = (long long)c.sequence_len * c.mini_batch;
+    if (S % 128) return fail(FM_EINVAL, "S = sequence_len*mini_batch = %lld must be a multiple of 128", S);
+    if (S > (1ll << 24)) return fail(FM_EINVAL, "S = %lld too large", S);
+    if (c.num_experts < 1 || c.num_experts > 1024) return fail(FM_EINVAL, "num_experts must be in [1, 1024]");
+    if (c.expert_top_k < 1 || c.expert_top_k > c.num_experts || c.expert_top_k > 8)
+        return fail(FM_EINVAL, "expert_top_k must be in [1, min(num_experts, 8)]");
+    if (world < 1 || world > FM_MAX_WORLD) return fail(FM_EINVAL, "world size %d not in [1, %d]", world, FM_MAX_WORLD);
+    if (c.num_experts % world) return fail(FM_EINVAL, "num_experts=%d not divisible by world=%d", c.num_experts, world);
+    d->S = (int)S;
+    d->H = c.hidden_size;
+    d->E = c.num_experts;
+    d->P = c.intermediate_size;
+    d->PX = ceil_div(c.num_experts, 64) * 64;
+    d->element_size = 2;
+    d->k = c.expert_top_k;
+    const long long ec = (long long)(c.drop_tokens ? ceil_div((int)S, c.num_experts) : (int)S) * c.capacity_factor *
+                         c.expert_top_k;
+    if (ec > (1ll << 24)) return fail(FM_EINVAL, "expert capacity %lld too large", ec);
+    d->EC = (int)ec;
+    d->pEC = ceil_div(d->EC, 128) * 128;
+    d->TCM = d->pEC / 128;
+    d->world = world;
+    d->num_local_experts = c.num_experts / world;
+    return FM_OK;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    const size_t bytes = count * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(FM_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    if (zero) {
+        e = cudaMemset(q, 0, bytes ? bytes : 16);
+        if (e != cudaSuccess) return fail(FM_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    *p = static_cast<T*>(q);
+    return FM_OK;
+}
+
+void set_peer_pointers(const fm_ctx* c, fm::FmParams& p) {
+    for (int r = 0; r < c->d.world; ++r) {
+        char* b = static_cast<char*>(c->peer_base[r]);
+        p.peer_recv_x[r] = reinterpret_cast<__nv_bfloat16*>(b + c->off_recv_x);
+        p.peer_ret_y[r] = reinterpret_cast<__nv_bfloat16*>(b + c->off_ret_y);
+        p.peer_recv_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_recv_flag);
+        p.peer_ret_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_ret_flag);
+    }
+}
+
+int check_kernel_status(fm_ctx* c) {
+    if (c->dbg_host != nullptr && c->dbg_host->code != 0) {
+        static const char* names[] = {"none", "smem-full mbarrier", "smem-empty mbarrier", "tmem-full mbarrier",
+                                      "tmem-empty mbarrier", "sched-full mbarrier", "sched-empty mbarrier",
+                                      "grid barrier", "dispatch flag (packet never arrived)", "GEMM0 row-block counter",
+                                      "return flag (expert output never arrived)"};
+        const fm::DebugRecord r = *c->dbg_host;
+        const char* nm = r.code < sizeof(names) / sizeof(names[0]) ? names[r.code] : "unknown";
+        return fail(FM_EKERNEL,
+                    "kernel wait timed out on %s: block %u thread %u info=(%u,%u,%u) waited %.1f ms (rank %d, launch %llu)",
+                    nm, r.block, r.thread, r.info0, r.info1, r.info2, (double)r.waited_ns * 1e-6, c->d.rank,
+                    (unsigned long long)c->launches);
+    }
+    return FM_OK;
+}
+
+int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, const void* bias_up,
+           const void* bias_down, void* out, cudaStream_t stream, uint32_t phase_mask) {
+    if (c == nullptr) return fail(FM_EINVAL, "null context");
+    if (x == nullptr || gate_w == nullptr || expert_w == nullptr || out == nullptr)
+        return fail(FM_EINVAL, "x, gate_w, expert_w and out must be non-null device pointers");
+    if (!c->attached) return fail(FM_ESTATE, "peers not attached: call fm_symm_attach_ipc/ptrs before fm_moe_forward");
+    if ((phase_mask & 1u) == 0u && c->d.world != 1) return fail(FM_EINVAL, "partial-phase launches are single-rank only");
+    if ((phase_mask & 1u) == 0u && c->epoch == 0) return fail(FM_ESTATE, "no previous routing to reuse");
+    FM_CUDA(cudaSetDevice(c->device));
+    const fm_dims_t& d = c->d;
+    const int nLx = d.num_local_experts;
+    int rc;
+    if (!c->tm_static_ready) {
+        if ((rc = make_tmap(&c->tm_a0, static_cast<char*>(c->symm) + c->off_recv_x, (uint64_t)c->num_pkts * d.pEC, d.H,
+                            fm::BLOCK_M)))
+            return rc;
+        if ((rc = make_tmap(&c->tm_a1, c->hidden, (uint64_t)c->num_pkts * d.pEC, d.P, fm::BLOCK_M))) return rc;
+        c->tm_static_ready = true;
+    }
+    if (c->cached_expert_w != expert_w) {
+        // expert_weights [nLx, 2, P, H]: [i,0] is W_up [P,H]; [i,1] is the same P*H block viewed as W_down [H,P]
+        // (python_bindings.cu:104-119).  One tensor map per GEMM over the whole tensor with a per-expert row stride
+        // of 2*P (resp. 2*H) rows is not expressible in 2-D, so rows are addressed as [nLx*2*P, H] / [nLx*2*H, P]:
+        // expert i's W_up starts at row i*2*P, its W_down at row (i*2+1)*H of the [.,P] view.
+        if ((rc = make_tmap(&c->tm_b0, expert_w, (uint64_t)nLx * 2 * d.P, d.H, fm::BLOCK_N))) return rc;
+        if ((rc = make_tmap(&c->tm_b1, expert_w, (uint64_t)nLx * 2 * d.H, d.P, fm::BLOCK_N))) return rc;
+        c->cached_expert_w = expert_w;
+    }
+    fm::FmParams p;
+    memset(&p, 0, sizeof(p));
+    p.tm_a0 = c->tm_a0; p.tm_b0 = c->tm_b0; p.tm_a1 = c->tm_a1; p.tm_b1 = c->tm_b1;
+    p.S = d.S; p.H = d.H; p.P = d.P; p.E = d.E; p.k = d.k; p.W = d.world; p.rank = d.rank; p.nLx = nLx;
+    p.EC = d.EC; p.pEC = d.pEC; p.TCM = d.TCM; p.act = c->cfg.hidden_act;
+    p.TN0 = c->TN0; p.TN1 = c->TN1; p.tpc = c->tpc; p.num_pkts = c->num_pkts; p.num_blocks = c->num_blocks;
+    p.total_items = c->total_items;
+    if (phase_mask & 1u) {
+        c->epoch += 1;
+        c->bar_count += (unsigned long long)c->grid;
+    }
+    p.epoch = c->epoch;
+    p.phase_mask = phase_mask;
+    p.bar_target = c->bar_count;
+    p.timeout_ns = c->timeout_ns;
+    p.x = static_cast<const __nv_bfloat16*>(x);
+    p.wg = static_cast<const __nv_bfloat16*>(gate_w);
+    p.b_up = static_cast<const __nv_bfloat16*>(bias_up);
+    p.b_down = static_cast<const __nv_bfloat16*>(bias_down);
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.topk_idx = c->topk_idx; p.topk_w = c->topk_w; p.mcw = c->mcw; p.slot = c->slot; p.counts = c->counts;
+    p.gate_out = c->gate_out; p.chunk_counts = c->chunk_counts;
+    p.disp_done = c->ctrl; p.claim = c->ctrl + 1;
+    p.grid_bar = reinterpret_cast<unsigned long long*>(c->ctrl + 2);
+    p.g0_done = c->g0_done; p.g1_done = c->g1_done; p.recv_cnt = c->recv_cnt; p.blocks = c->blocks;
+    p.hidden = c->hidden;
+    char* sb = static_cast<char*>(c->symm);
+    p.recv_x = reinterpret_cast<__nv_bfloat16*>(sb + c->off_recv_x);
+    p.ret_y = reinterpret_cast<__nv_bfloat16*>(sb + c->off_ret_y);
+    p.recv_flag = reinterpret_cast<unsigned long long*>(sb + c->off_recv_flag);
+    p.ret_flag = reinterpret_cast<unsigned long long*>(sb + c->off_ret_flag);
+    set_peer_pointers(c, p);
+    p.dbg = c->dbg_dev;
+
+    void* args[] = {&p};
+    FM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel), dim3(c->grid),
+                                        dim3(fm::NUM_THREADS), args, (size_t)fm::SMEM_BYTES, stream));
+    c->launches += 1;
+    return FM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================================
+extern "C" {
+
+FM_API const char* fm_last_error(void) { return g_err.c_str(); }
+FM_API const char* fm_version(void) { return "flashmoe_b200 0.1.0 (sm_100a, tcgen05/TMEM/TMA)"; }
+
+FM_API int fm_compiled_config(fm_config_t* out) {
+    if (out == nullptr) return fail(FM_EINVAL, "null output");
+    out->capacity_factor = FM_CFG_CAPACITY_FACTOR;
+    out->drop_tokens = FM_CFG_DROP_TOKENS;
+    out->expert_top_k = FM_CFG_EXPERT_TOP_K;
+    out->global_batch = FM_CFG_GLOBAL_BATCH;
+    out->is_training = FM_CFG_IS_TRAINING;
+    out->hidden_act = FM_CFG_HIDDEN_ACT;
+    out->hidden_size = FM_CFG_HIDDEN_SIZE;
+    out->intermediate_size = FM_CFG_INTERMEDIATE_SIZE;
+    out->mini_batch = FM_CFG_MINI_BATCH;
+    out->moe_frequency = FM_CFG_MOE_FREQUENCY;
+    out->num_experts = FM_CFG_NUM_EXPERTS;
+    out->num_layers = FM_CFG_NUM_LAYERS;
+    out->sequence_len = FM_CFG_SEQUENCE_LEN;
+    out->torch_dtype = FM_CFG_TORCH_DTYPE;
+    out->vocab_size = FM_CFG_VOCAB_SIZE;
+    return FM_OK;
+}
+
+FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm_ctx_t** out) {
+    if (out == nullptr) return fail(FM_EINVAL, "null output");
+    *out = nullptr;
+    fm_config_t c;
+    if (cfg != nullptr) c = *cfg;
+    else fm_compiled_config(&c);
+    fm_dims_t d;
+    memset(&d, 0, sizeof(d));
+    int rc = validate_config(c, world, &d);
+    if (rc) return rc;
+    if (rank < 0 || rank >= world) return fail(FM_EINVAL, "rank %d not in [0, %d)", rank, world);
+    d.rank = rank;
+
+    int ndev = 0;
+    FM_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(FM_EINVAL, "device %d not in [0, %d)", device, ndev);
+    FM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(FM_ECUDA, "device %d is sm_%d%d; this library contains sm_100a code only (tcgen05/TMEM/TMA)", device,
+                    prop.major, prop.minor);
+    int coop = 0;
+    FM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) return fail(FM_ECUDA, "device does not support cooperative launch");
+    d.num_sms = prop.multiProcessorCount;
+    d.smem_bytes = fm::SMEM_BYTES;
+
+    FM_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fm::SMEM_BYTES));
+    int occ = 0;
+    FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fm::fm_moe_forward_kernel, fm::NUM_THREADS,
+                                                          (size_t)fm::SMEM_BYTES));
+    if (occ < 1) return fail(FM_ECUDA, "kernel does not fit on an SM (smem %d B)", fm::SMEM_BYTES);
+
+    fm_ctx* ctx = new fm_ctx();
+    ctx->cfg = c;
+    ctx->d = d;
+    ctx->device = device;
+    ctx->grid = d.num_sms;  // one persistent CTA per SM; all co-resident (spin waits + grid barrier)
+    ctx->tpc = ceil_div(d.S, ctx->grid);
+    if ((long long)ctx->tpc * d.k > fm::G_SEL_MAX) {
+        delete ctx;
+        return fail(FM_EINVAL, "tokens-per-CTA * k = %d exceeds the router scratch (%d)", ctx->tpc * d.k, fm::G_SEL_MAX);
+    }
+    const int nLx = d.num_local_experts;
+    ctx->TN0 = ceil_div(d.P, fm::BLOCK_N);
+    ctx->TN1 = ceil_div(d.H, fm::BLOCK_N);
+    ctx->num_pkts = world * nLx;
+
+    // work-item blocks: own rank's packets first, then rank+1, ...; GEMM1 lags GEMM0 by one packet
+    std::vector<int> order;
+    for (int j = 0; j < world; ++j) {
+        const int src = (rank + j) % world;
+        for (int le = 0; le < nLx; ++le) order.push_back(src * nLx + le);
+    }
+    std::vector<fm::TileBlock> blocks;
+    int start = 0;
+    auto push = [&](int kind, int pkt) {
+        fm::TileBlock b;
+        b.kind = kind; b.pkt = pkt; b.start = start; b.pad = 0;
+        blocks.push_back(b);
+        start += d.TCM * (kind == 0 ? ctx->TN0 : ctx->TN1);
+    };
+    for (size_t i = 0; i < order.size(); ++i) {
+        push(0, order[i]);
+        if (i >= 1) push(1, order[i - 1]);
+    }
+    push(1, order.back());
+    ctx->num_blocks = (int)blocks.size();
+    ctx->total_items = start;
+    fm::TileBlock sentinel;
+    sentinel.kind = -1; sentinel.pkt = 0; sentinel.start = start; sentinel.pad = 0;
+    blocks.push_back(sentinel);
+
+#define FM_TRY(expr)          \
+    do {                      \
+        rc = (expr);          \
+        if (rc) {             \
+            fm_destroy(ctx);  \
+            return rc;        \
+        }                     \
+    } while (0)
+#define FM_TRY_CUDA(expr)                                                                             \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            fm_destroy(ctx);                                                                          \
+            return fail(FM_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                    \
+        }                                                                                             \
+    } while (0)
+
+    FM_TRY(dev_alloc(&ctx->topk_idx, (size_t)d.S * d.k));
+    FM_TRY(dev_alloc(&ctx->topk_w, (size_t)d.S * d.k));
+    FM_TRY(dev_alloc(&ctx->mcw, (size_t)d.S));
+    FM_TRY(dev_alloc(&ctx->slot, (size_t)d.S * d.k));
+    FM_TRY(dev_alloc(&ctx->counts, (size_t)d.E));
+    FM_TRY(dev_alloc(&ctx->gate_out, (size_t)d.S * d.E));
+    FM_TRY(dev_alloc(&ctx->chunk_counts, (size_t)ctx->grid * d.E));
+    FM_TRY(dev_alloc(&ctx->ctrl, 8));
+    FM_TRY(dev_alloc(&ctx->g0_done, (size_t)ctx->num_pkts * d.TCM));
+    FM_TRY(dev_alloc(&ctx->g1_done, (size_t)ctx->num_pkts * d.TCM));
+    FM_TRY(dev_alloc(&ctx->recv_cnt, (size_t)ctx->num_pkts));
+    FM_TRY(dev_alloc(&ctx->blocks, blocks.size(), false));
+    FM_TRY_CUDA(cudaMemcpy(ctx->blocks, blocks.data(), blocks.size() * sizeof(fm::TileBlock), cudaMemcpyHostToDevice));
+    FM_TRY(dev_alloc(&ctx->hidden, (size_t)ctx->num_pkts * d.pEC * d.P));
+
+    // symmetric slab: [recv_x | ret_y | recv_flag | ret_flag]  (reference heap + flags, bootstrap.cuh:348-362)
+    size_t off = 0;
+    ctx->off_recv_x = off; off = align_up(off + (size_t)ctx->num_pkts * d.pEC * d.H * 2, 1024);
+    ctx->off_ret_y = off;  off = align_up(off + (size_t)d.E * d.pEC * d.H * 2, 1024);
+    ctx->off_recv_flag = off; off = align_up(off + (size_t)ctx->num_pkts * 8, 1024);
+    ctx->off_ret_flag = off;  off = align_up(off + (size_t)d.E * d.TCM * 8, 1024);
+    ctx->symm_bytes = off;
+    {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, ctx->symm_bytes);
+        if (e != cudaSuccess) {
+            fm_destroy(ctx);
+            return fail(FM_ENOMEM, "cudaMalloc(symmetric slab, %zu bytes) failed: %s", ctx->symm_bytes, cudaGetErrorString(e));
+        }
+        ctx->symm = q;
+        FM_TRY_CUDA(cudaMemset(q, 0, ctx->symm_bytes));
+    }
+    FM_TRY_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->dbg_host), sizeof(fm::DebugRecord), cudaHostAllocMapped));
+    memset(ctx->dbg_host, 0, sizeof(fm::DebugRecord));
+    FM_TRY_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->dbg_dev), ctx->dbg_host, 0));
+    FM_TRY_CUDA(cudaDeviceSynchronize());
+    if (world == 1) {
+        ctx->peer_base[0] = ctx->symm;
+        ctx->attached = true;
+    }
+#undef FM_TRY
+#undef FM_TRY_CUDA
+    *out = ctx;
+    return FM_OK;
+}
+
+FM_API int fm_destroy(fm_ctx_t* ctx) {
+    if (ctx == nullptr) return FM_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ctx->d.world; ++r)
+        if (ctx->peer_opened[r] && ctx->peer_base[r] != nullptr) cudaIpcCloseMemHandle(ctx->peer_base[r]);
+    void* bufs[] = {ctx->topk_idx, ctx->topk_w, ctx->mcw, ctx->slot, ctx->counts, ctx->gate_out, ctx->chunk_counts,
+                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->x_stage,
+                    ctx->out_stage};
+    for (void* b : bufs)
+        if (b != nullptr) cudaFree(b);
+    if (ctx->symm != nullptr && !ctx->symm_external) cudaFree(ctx->symm);
+    if (ctx->dbg_host != nullptr) cudaFreeHost(ctx->dbg_host);
+    delete ctx;
+    return FM_OK;
+}
+
+FM_API int fm_get_dims(const fm_ctx_t* ctx, fm_dims_t* out) {
+    if (ctx == nullptr || out == nullptr) return fail(FM_EINVAL, "null argument");
+    *out = ctx->d;
+    return FM_OK;
+}
+
+FM_API int fm_num_local_experts(const fm_ctx_t* ctx) {
+    if (ctx == nullptr) return fail(FM_EINVAL, "null context");
+    return ctx->d.num_local_experts;
+}
+
+FM_API int fm_symm_size(const fm_ctx_t* ctx, size_t* bytes) {
+    if (ctx == nullptr || bytes == nullptr) return fail(FM_EINVAL, "null argument");
+    *bytes = ctx->symm_bytes;
+    return FM_OK;
+}
+
+FM_API int fm_symm_local_ptr(const fm_ctx_t* ctx, void** base) {
+    if (ctx == nullptr || base == nullptr) return fail(FM_EINVAL, "null argument");
+    *base = ctx->symm;
+    return FM_OK;
+}
+
+FM_API int fm_symm_use_external(fm_ctx_t* ctx, void* base, size_t bytes) {
+    if (ctx == nullptr || base == nullptr) return fail(FM_EINVAL, "null argument");
+    if (ctx->attached && ctx->d.world > 1) return fail(FM_ESTATE, "already attached");
+    if (bytes < ctx->symm_bytes) return fail(FM_EINVAL, "external slab too small: %zu < %zu", bytes, ctx->symm_bytes);
+    if (reinterpret_cast<uintptr_t>(base) % 1024) return fail(FM_EINVAL, "external slab must be 1 KiB aligned");
+    FM_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->symm != nullptr && !ctx->symm_external) FM_CUDA(cudaFree(ctx->symm));
+    ctx->symm = base;
+    ctx->symm_external = true;
+    ctx->tm_static_ready = false;
+    if (ctx->d.world == 1) ctx->peer_base[0] = base;
+    return FM_OK;
+}
+
+FM_API int fm_symm_export(fm_ctx_t* ctx, void* handle_out) {
+    if (ctx == nullptr || handle_out == nullptr) return fail(FM_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == FM_IPC_HANDLE_BYTES, "IPC handle size");
+    FM_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    FM_CUDA(cudaIpcGetMemHandle(&h, ctx->symm));
+    memcpy(handle_out, &h, sizeof(h));
+    return FM_OK;
+}
+
+FM_API int fm_symm_attach_ipc(fm_ctx_t* ctx, const void* all_handles) {
+    if (ctx == nullptr || all_handles == nullptr) return fail(FM_EINVAL, "null argument");
+    if (ctx->attached && ctx->d.world > 1) return fail(FM_ESTATE, "already attached");
+    FM_CUDA(cudaSetDevice(ctx->device));
+    const char* hs = static_cast<const char*>(all_handles);
+    for (int r = 0; r < ctx->d.world; ++r) {
+        if (r == ctx->d.rank) {
+            ctx->peer_base[r] = ctx->symm;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, hs + (size_t)r * FM_IPC_HANDLE_BYTES, sizeof(h));
+        void* ptr = nullptr;
+        FM_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_base[r] = ptr;
+        ctx->peer_opened[r] = true;
+    }
+    ctx->attached = true;
+    return FM_OK;
+}
+
+FM_API int fm_symm_attach_ptrs(fm_ctx_t* ctx, void* const* peer_bases) {
+    if (ctx == nullptr || peer_bases == nullptr) return fail(FM_EINVAL, "null argument");
+    for (int r = 0; r < ctx->d.world; ++r) {
+        if (peer_bases[r] == nullptr) return fail(FM_EINVAL, "peer base %d is null", r);
+        ctx->peer_base[r] = (r == ctx->d.rank) ? ctx->symm : peer_bases[r];
+    }
+    ctx->attached = true;
+    return FM_OK;
+}
+
+FM_API int fm_moe_forward(fm_ctx_t* ctx, const void* x, const void* gate_w, const void* expert_w, const void* bias_up,
+                          const void* bias_down, void* out, void* stream) {
+    return launch(ctx, x, gate_w, expert_w, bias_up, bias_down, out, static_cast<cudaStream_t>(stream), 7u);
+}
+
+FM_API int fm_debug_forward(fm_ctx_t* ctx, const void* x, const void* gate_w, const void* expert_w,
+                            const void* bias_up, const void* bias_down, void* out, void* stream, uint32_t phase_mask) {
+    if (phase_mask == 0 || phase_mask > 7u) return fail(FM_EINVAL, "phase_mask must be in [1, 7]");
+    return launch(ctx, x, gate_w, expert_w, bias_up, bias_down, out, static_cast<cudaStream_t>(stream), phase_mask);
+}
+
+FM_API int fm_moe_forward_host(fm_ctx_t* ctx, const void* x_host, const void* gate_w, const void* expert_w,
+                               const void* bias_up, const void* bias_down, void* out_host, void* stream) {
+    if (ctx == nullptr || x_host == nullptr || out_host == nullptr) return fail(FM_EINVAL, "null argument");
+    FM_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ctx->d.S * ctx->d.H * 2;
+    int rc;
+    if (ctx->x_stage == nullptr && (rc = dev_alloc(&ctx->x_stage, bytes / 2, false))) return rc;
+    if (ctx->out_stage == nullptr && (rc = dev_alloc(&ctx->out_stage, bytes / 2, false))) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    FM_CUDA(cudaMemcpyAsync(ctx->x_stage, x_host, bytes, cudaMemcpyHostToDevice, s));
+    if ((rc = launch(ctx, ctx->x_stage, gate_w, expert_w, bias_up, bias_down, ctx->out_stage, s, 7u))) return rc;
+    FM_CUDA(cudaMemcpyAsync(out_host, ctx->out_stage, bytes, cudaMemcpyDeviceToHost, s));
+    cudaError_t e = cudaStreamSynchronize(s);
+    if ((rc = check_kernel_status(ctx))) return rc;
+    if (e != cudaSuccess) return fail(FM_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    return FM_OK;
+}
+
+FM_API int fm_check(fm_ctx_t* ctx) {
+    if (ctx == nullptr) return fail(FM_EINVAL, "null context");
+    return check_kernel_status(ctx);
+}
+
+FM_API int fm_set_timeout_ms(fm_ctx_t* ctx, uint32_t ms) {
+    if (ctx == nullptr) return fail(FM_EINVAL, "null context");
+    ctx->timeout_ns = (unsigned long long)ms * 1000000ull;
+    return FM_OK;
+}
+
+FM_API uint64_t fm_launch_count(const fm_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
+
+static int buffer_desc(const fm_ctx_t* c, int which, const void** ptr, size_t* bytes) {
+    const fm_dims_t& d = c->d;
+    const char* sb = static_cast<const char*>(c->symm);
+    switch (which) {
+        case FM_BUF_TOPK_IDX: *ptr = c->topk_idx; *bytes = (size_t)d.S * d.k * 4; break;
+        case FM_BUF_TOPK_W: *ptr = c->topk_w; *bytes = (size_t)d.S * d.k * 2; break;
+        case FM_BUF_MCW: *ptr = c->mcw; *bytes = (size_t)d.S * 4; break;
+        case FM_BUF_SLOT: *ptr = c->slot; *bytes = (size_t)d.S * d.k * 4; break;
+        case FM_BUF_COUNTS: *ptr = c->counts; *bytes = (size_t)d.E * 4; break;
+        case FM_BUF_RECV_X: *ptr = sb + c->off_recv_x; *bytes = (size_t)c->num_pkts * d.pEC * d.H * 2; break;
+        case FM_BUF_HIDDEN: *ptr = c->hidden; *bytes = (size_t)c->num_pkts * d.pEC * d.P * 2; break;
+        case FM_BUF_RET_Y: *ptr = sb + c->off_ret_y; *bytes = (size_t)d.E * d.pEC * d.H * 2; break;
+        case FM_BUF_GATE_OUT: *ptr = c->gate_out; *bytes = (size_t)d.S * d.E * 2; break;
+        case FM_BUF_RECV_CNT: *ptr = c->recv_cnt; *bytes = (size_t)c->num_pkts * 4; break;
+        default: return fail(FM_EINVAL, "unknown buffer id %d", which);
+    }
+    return FM_OK;
+}
+
+FM_API int fm_buffer_bytes(const fm_ctx_t* ctx, int which, size_t* bytes) {
+    if (ctx == nullptr || bytes == nullptr) return fail(FM_EINVAL, "null argument");
+    const void* p;
+    return buffer_desc(ctx, which, &p, bytes);
+}
+
+FM_API int fm_read_buffer(fm_ctx_t* ctx, int which, void* host_dst, size_t bytes) {
+    if (ctx == nullptr || host_dst == nullptr) return fail(FM_EINVAL, "null argument");
+    const void* p;
+    size_t n;
+    int rc = buffer_desc(ctx, which, &p, &n);
+    if (rc) return rc;
+    if (bytes != n) return fail(FM_EINVAL, "buffer %d holds %zu bytes, caller asked for %zu", which, n, bytes);
+    FM_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaDeviceSynchronize();
+    if ((rc = check_kernel_status(ctx))) return rc;
+    if (e != cudaSuccess) return fail(FM_ECUDA, "cudaDeviceSynchronize failed: %s", cudaGetErrorString(e));
+    FM_CUDA(cudaMemcpy(host_dst, p, n, cudaMemcpyDeviceToHost));
+    return FM_OK;
+}
+
+}  // extern "C"

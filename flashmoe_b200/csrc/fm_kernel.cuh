@@ -1,0 +1,715 @@
+// fm_kernel.cuh -- the fused persistent MoE-forward kernel for sm_100a.
+//
+// One launch = one MoE layer forward on this rank (reference: flashmoe::moe::forward, csrc/include/flashmoe/moe/moe.cuh:77-144):
+//
+//   phase G  gate      x.Wg^T -> online softmax -> top-k -> capacity slots          (reference moe/gate.cuh:473-720)
+//            grid barrier (the only one, like the reference's gate.cuh:761)
+//   phase D  dispatch  token rows -> owner rank's receive buffer over NVLink + flag  (reference os/packet.cuh:21-286)
+//   phase F  expert FFN  persistent tcgen05 tile loop: GEMM0(+bias+act) -> h, GEMM1(+bias) -> source rank's return
+//            buffer + per-row-block flag                                            (reference os/processor/processor.cuh:340-468,
+//                                                                                    685-750; the OS CTA of os/os.cuh, scheduler.cuh,
+//                                                                                    subscriber.cuh is replaced by an atomic tile
+//                                                                                    claim + flag waits inside every CTA)
+//   phase C  combine   per token: gather the k returned rows, scale, bf16-accumulate (reference processor.cuh:27-205)
+//
+// CTA = 256 threads, one CTA per SM, all co-resident (cooperative launch).  In phase F the warps specialise:
+// warp 0 = tile claimer + TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+// (TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced 16-byte global / peer stores).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/flashmoe_b200.h"
+#include "fm_ptx.cuh"
+
+namespace fm {
+
+constexpr int BLOCK_M = 128;   // token rows per tile (= reference BLOCK_M)
+constexpr int BLOCK_N = 256;   // output columns per tile (one tcgen05.mma N)
+constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NSCHED = 4;
+constexpr int NUM_THREADS = 256;
+constexpr int NUM_WARPS = NUM_THREADS / 32;
+constexpr int EPI_WARP0 = 4;   // warps 4..7 (warp % 4 selects the TMEM lane quarter)
+constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators
+
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                  // 16 KiB
+constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;                  // 32 KiB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;            // 48 KiB
+constexpr int EPI_ROW_BYTES = 144;                                    // 128 B of payload + 16 B pad (bank spread)
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
+constexpr int OFF_EPI = STAGES * STAGE_BYTES;                         // 196608
+constexpr int OFF_BARS = OFF_EPI + 4 * EPI_WARP_BYTES;                // 215040
+constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NSCHED;                 // 20
+constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 215200
+constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 32;                  // 215328
+constexpr int OFF_MISC = OFF_TMEM_PTR + 16;                           // 215344
+constexpr int SMEM_USED = OFF_MISC + 64;
+constexpr int SMEM_BYTES = SMEM_USED + 1024;                          // + slack for manual 1 KiB alignment
+
+// gate-phase aliases of the (not yet used) pipeline stage area
+constexpr int G_OFF_WG = 0;              // bf16 [EG][Hc]           <= 64 KiB
+constexpr int G_WG_BYTES = 65536;
+constexpr int G_OFF_LOGIT = 65536;       // f32  [TS][E+1]          <= 64 KiB
+constexpr int G_LOGIT_BYTES = 65536;
+constexpr int G_OFF_SEL = 131072;        // int16 sel_e[tpc*k] then int32 rank[tpc*k]   <= 48 KiB
+constexpr int G_SEL_MAX = 8192;          // max tpc*k
+constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E]        <= 4 KiB (E <= 1024)
+static_assert(G_OFF_BASE + 4096 <= OFF_EPI, "gate scratch must fit in the stage area");
+
+struct TileBlock {  // one contiguous run of work items: all tiles of one GEMM of one packet
+    int kind;       // 0 = GEMM0 (x.W_up^T), 1 = GEMM1 (h.W_down^T)
+    int pkt;        // local packet index = src * nLx + le
+    int start;      // first global item id of this block
+    int pad;
+};
+
+struct FmParams {
+    CUtensorMap tm_a0;  // recv_x  as [W*nLx*pEC, H]  box {64, 128}
+    CUtensorMap tm_b0;  // expert_weights as [nLx*2*P, H]  box {64, 256}  (W_up rows)
+    CUtensorMap tm_a1;  // hidden  as [W*nLx*pEC, P]  box {64, 128}
+    CUtensorMap tm_b1;  // expert_weights as [nLx*2*H, P]  box {64, 256}  (W_down rows)
+    int S, H, P, E, k, W, rank, nLx, EC, pEC, TCM, act;
+    int TN0, TN1, tpc, num_pkts, num_blocks, total_items;
+    unsigned int epoch, phase_mask;
+    unsigned long long bar_target, timeout_ns;
+    const __nv_bfloat16 *x, *wg, *b_up, *b_down;
+    __nv_bfloat16* out;
+    int* topk_idx;             // [S,k]
+    __nv_bfloat16* topk_w;     // [S,k]
+    float* mcw;                // [S]
+    int* slot;                 // [S,k]
+    int* counts;               // [E]
+    __nv_bfloat16* gate_out;   // [S,E]
+    int* chunk_counts;         // [grid, E]
+    unsigned int* disp_done;   // [1]
+    unsigned int* claim;       // [1]
+    unsigned int* g0_done;     // [num_pkts, TCM]
+    unsigned int* g1_done;     // [num_pkts, TCM]
+    unsigned long long* grid_bar;
+    int* recv_cnt;             // [num_pkts]
+    const TileBlock* blocks;   // [num_blocks + 1] (sentinel start = total_items)
+    __nv_bfloat16* hidden;     // [W*nLx*pEC, P]
+    __nv_bfloat16* recv_x;     // local symmetric: [W, nLx, pEC, H]
+    unsigned long long* recv_flag;  // [W, nLx]
+    __nv_bfloat16* ret_y;      // [E, pEC, H]
+    unsigned long long* ret_flag;   // [E, TCM]
+    __nv_bfloat16* peer_recv_x[FM_MAX_WORLD];
+    unsigned long long* peer_recv_flag[FM_MAX_WORLD];
+    __nv_bfloat16* peer_ret_y[FM_MAX_WORLD];
+    unsigned long long* peer_ret_flag[FM_MAX_WORLD];
+    DebugRecord* dbg;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(const FmParams& p) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atom_acq_rel_gpu_add_u64(p.grid_bar, 1ull);
+        SpinGuard g;
+        while (ld_acquire_gpu_u64(p.grid_bar) < p.bar_target)
+            g.tick(p.dbg, p.timeout_ns, FM_TRAP_GRID_BARRIER, 0, 0, 0);
+    }
+    __syncthreads();
+}
+
+// sum over lanes of acc[i] ends up in lane i (31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_reduce(float (&acc)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? acc[j] : acc[j + off];
+            const float keep = upper ? acc[j + off] : acc[j];
+            acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return acc[0];
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+// ============================================================================================================
+// Phase G: router.  CTA b owns tokens [b*tpc, min(S, (b+1)*tpc)).
+//   logits[t,e] = sum_h x[t,h] * Wg_eff[e,h]       Wg_eff = gate_weights viewed flat as [E,H]  (moe.cuh:107-109)
+//   softmax with the reference's online recurrence and fast intrinsics (gate.cuh:575-584), top-k by k rounds of
+//   strict-'>' scans in ascending expert order on fp32 p (gate.cuh:654-670), mCw = sum of the picked p.
+//   Slots: ascending-token order within the CTA's chunk here; chunk bases after the grid barrier (a legal
+//   interleaving of the reference's BlockScan + atomicAdd(eC) order, gate.cuh:678-718).
+// ============================================================================================================
+__device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = p.E, H = p.H, k = p.k;
+    __nv_bfloat16* wg_s = reinterpret_cast<__nv_bfloat16*>(smem + G_OFF_WG);
+    float* logit_s = reinterpret_cast<float*>(smem + G_OFF_LOGIT);
+    int16_t* sel_e = reinterpret_cast<int16_t*>(smem + G_OFF_SEL);
+    int* rank_s = reinterpret_cast<int*>(smem + G_OFF_SEL + G_SEL_MAX * 2);
+
+    const int EG = E < 128 ? E : 128;                      // experts staged per group
+    int Hc = (G_WG_BYTES / (EG * 2)) & ~255;               // H columns staged per chunk (multiple of 256)
+    if (Hc > H) Hc = H;
+    const int ldl = E + 1;                                  // padded logits row (bank spread for thread-per-row)
+    int TS = G_LOGIT_BYTES / (ldl * 4);                     // tokens per sub-chunk
+    if (TS > n_tok) TS = n_tok;
+
+    for (int s0 = 0; s0 < n_tok; s0 += TS) {
+        const int n_sub = min(TS, n_tok - s0);
+        for (int i = tid; i < n_sub * ldl; i += NUM_THREADS) logit_s[i] = 0.0f;
+        for (int eg0 = 0; eg0 < E; eg0 += EG) {
+            const int eg_len = min(EG, E - eg0);
+            for (int hc0 = 0; hc0 < H; hc0 += Hc) {
+                const int hc_len = min(Hc, H - hc0);
+                __syncthreads();  // previous users of wg_s are done (also orders the logit_s zero fill)
+                // stage Wg_eff[eg0 .. eg0+eg_len, hc0 .. hc0+hc_len) -> wg_s[e][Hc], 16 B per thread-iteration
+                const int vec_per_row = hc_len >> 3;
+                for (int i = tid; i < eg_len * vec_per_row; i += NUM_THREADS) {
+                    const int e = i / vec_per_row, v = i - e * vec_per_row;
+                    const uint4 w = ld_global_nc_v4(p.wg + (size_t)(eg0 + e) * H + hc0 + v * 8);
+                    *reinterpret_cast<uint4*>(wg_s + (size_t)e * Hc + v * 8) = w;
+                }
+                __syncthreads();
+                for (int ti = warp; ti < n_sub; ti += NUM_WARPS) {
+                    const __nv_bfloat16* xr = p.x + (size_t)(t0 + s0 + ti) * H + hc0;
+                    for (int sub = 0; sub * 32 < eg_len; ++sub) {
+                        const int ne = min(32, eg_len - sub * 32);
+                        float acc[32];
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
+                        for (int p0 = 0; p0 < hc_len; p0 += 256) {
+                            const int h = p0 + lane * 8;
+                            if (h < hc_len) {
+                                float xf[8];
+                                unpack8(ld_global_nc_v4(xr + h), xf);
+                                const __nv_bfloat16* wrow = wg_s + (size_t)(sub * 32) * Hc + h;
+#pragma unroll
+                                for (int e = 0; e < 32; ++e) {
+                                    if (e < ne) {
+                                        float wf[8];
+                                        unpack8(*reinterpret_cast<const uint4*>(wrow + (size_t)e * Hc), wf);
+#pragma unroll
+                                        for (int q = 0; q < 8; ++q) acc[e] = fmaf(xf[q], wf[q], acc[e]);
+                                    }
+                                }
+                            }
+                        }
+                        const float tot = warp_transpose_reduce(acc, lane);
+                        if (lane < ne) logit_s[ti * ldl + eg0 + sub * 32 + lane] += tot;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // thread-per-token softmax + top-k, the same per-thread recurrence the reference runs after its transpose
+        for (int ti = tid; ti < n_sub; ti += NUM_THREADS) {
+            float* l = logit_s + ti * ldl;
+            const int t = t0 + s0 + ti;
+            float dI = 0.0f, mI = -INFINITY;
+            for (int e = 0; e < E; ++e) {
+                const float pM = mI;
+                mI = fmaxf(mI, l[e]);
+                dI = fmaf(dI, fast_expf(pM - mI), fast_expf(l[e] - mI));
+            }
+            for (int e = 0; e < E; ++e) {
+                const float pe = __fdividef(fast_expf(l[e] - mI), dI);
+                l[e] = pe;
+                p.gate_out[(size_t)t * E + e] = __float2bfloat16_rn(pe);
+            }
+            int picked[8];
+            float sum = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                picked[i] = -1;
+                if (i < k) {
+                    float sV = -INFINITY;
+                    int sIdx = 0;
+                    for (int j = 0; j < E; ++j) {
+                        bool taken = false;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) taken |= (q < i) && (picked[q] == j);
+                        if (l[j] > sV && !taken) {
+                            sIdx = j;
+                            sV = l[j];
+                        }
+                    }
+                    picked[i] = sIdx;
+                    sum += sV;
+                    p.topk_idx[(size_t)t * k + i] = sIdx;
+                    p.topk_w[(size_t)t * k + i] = __float2bfloat16_rn(sV);
+                    sel_e[(s0 + ti) * k + i] = (int16_t)sIdx;
+                }
+            }
+            p.mcw[t] = sum;
+        }
+        __syncthreads();
+    }
+    // position of every (token, pick) among this chunk's selections of the same expert, ascending token order
+    for (int e = tid; e < E; e += NUM_THREADS) {
+        int cnt = 0;
+        for (int i = 0; i < n_tok * k; ++i)
+            if (sel_e[i] == e) rank_s[i] = cnt++;
+        p.chunk_counts[(size_t)blockIdx.x * E + e] = cnt;
+    }
+}
+
+// ============================================================================================================
+// Phase D: dispatch (after the grid barrier).  slot = (selections of e by lower chunks) + rank in chunk; kept iff
+// slot < EC (gate.cuh:713-717).  Each warp copies whole token rows with 16-byte accesses straight into the owner
+// rank's receive buffer (peer-mapped, NVLink) -- the reference's P2P branch (os/packet.cuh:114-116,151-166).
+// The last CTA to finish publishes one 8-byte flag {epoch, rows} per expert (os/packet.cuh:214-237; a flag is
+// also sent for 0 rows, like the reference's "noop" signal).
+// ============================================================================================================
+__device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = p.E, H = p.H, k = p.k, G = gridDim.x;
+    const int16_t* sel_e = reinterpret_cast<const int16_t*>(smem + G_OFF_SEL);
+    const int* rank_s = reinterpret_cast<const int*>(smem + G_OFF_SEL + G_SEL_MAX * 2);
+    int* base_s = reinterpret_cast<int*>(smem + G_OFF_BASE);
+    unsigned int* misc = reinterpret_cast<unsigned int*>(smem + OFF_MISC);
+
+    for (int e = tid; e < E; e += NUM_THREADS) {
+        int b = 0;
+        for (int c = 0; c < (int)blockIdx.x; ++c) b += p.chunk_counts[(size_t)c * E + e];
+        base_s[e] = b;
+    }
+    __syncthreads();
+    for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
+        const int t = t0 + ti;
+        __nv_bfloat16* dst[8];
+        bool keep[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            keep[j] = false;
+            dst[j] = nullptr;
+            if (j < k) {
+                const int e = sel_e[ti * k + j];
+                const int s = base_s[e] + rank_s[ti * k + j];
+                if (lane == 0) p.slot[(size_t)t * k + j] = s;
+                keep[j] = s < p.EC;
+                const int owner = e / p.nLx, le = e - owner * p.nLx;
+                dst[j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[j] ? s : 0)) * H;
+            }
+        }
+        const __nv_bfloat16* src = p.x + (size_t)t * H;
+        for (int h = lane * 8; h < H; h += 256) {
+            const uint4 v = ld_global_nc_v4(src + h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < k && keep[j]) st_global_v4(dst[j] + h, v);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        fence_acq_rel_sys();  // this CTA's row stores (observed through the barrier) before the counter bump
+        const unsigned int old = atom_acq_rel_gpu_add_u32(p.disp_done, 1u);
+        misc[0] = (old == (unsigned int)G - 1u) ? 1u : 0u;
+        if (misc[0]) fence_acq_rel_sys();
+    }
+    __syncthreads();
+    if (misc[0]) {  // last CTA: every chunk's rows are out; publish counts to the owners
+        for (int e = tid; e < E; e += NUM_THREADS) {
+            int tot = 0;
+            for (int c = 0; c < G; ++c) tot += p.chunk_counts[(size_t)c * E + e];
+            p.counts[e] = tot;
+            const int rows = tot < p.EC ? tot : p.EC;
+            const int owner = e / p.nLx, le = e - owner * p.nLx;
+            st_release_sys_u64(p.peer_recv_flag[owner] + (size_t)p.rank * p.nLx + le,
+                               ((unsigned long long)p.epoch << 32) | (unsigned int)rows);
+        }
+    }
+}
+
+// ============================================================================================================
+// Phase F: expert FFN.  Work items (global order, claimed with one atomic counter):
+//   for packets in the order (own rank first, then rank+1, ...): GEMM0 tiles of packet j, then GEMM1 tiles of packet
+//   j-1 (one packet of lag so the h row-block a GEMM1 tile needs is normally complete when it is claimed).
+//   item -> (row block m fastest, column tile n).  A GEMM1 tile waits for g0_done[pkt][m] == TN0.
+// ============================================================================================================
+struct TileInfo {     // 32 bytes, written by the claimer, read by the MMA and epilogue warps
+    int kind;         // 0 GEMM0, 1 GEMM1, -1 stop
+    int pkt;          // local packet index src * nLx + le
+    int mblk;
+    int ntile;
+    int rows;         // valid rows in this row block
+    int src;
+    int le;
+    int pad;
+};
+
+__device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, uint64_t* bars) {
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* sched_full = bars + 2 * STAGES + 4;
+    uint64_t* sched_empty = sched_full + NSCHED;
+    TileInfo* ring = reinterpret_cast<TileInfo*>(smem + OFF_RING);
+    const int lane = threadIdx.x & 31;
+    int stage = 0, phase = 0, q = 0, qphase = 0, cursor = 0;
+    for (;;) {
+        int kind = -1, nk = 0, a_row = 0, b_row = 0;
+        if (lane == 0) {
+            TileInfo ti;
+            ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows = 0; ti.src = 0; ti.le = 0; ti.pad = 0;
+            for (;;) {
+                const int id = (int)atomicAdd(p.claim, 1u);
+                if (id >= p.total_items) break;
+                while (id >= p.blocks[cursor + 1].start) ++cursor;
+                const TileBlock blk = p.blocks[cursor];
+                const int local = id - blk.start;
+                const int mblk = local % p.TCM, nt = local / p.TCM;
+                const int src = blk.pkt / p.nLx, le = blk.pkt - src * p.nLx;
+                // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
+                unsigned long long f;
+                {
+                    SpinGuard g;
+                    while (((f = ld_acquire_sys_u64(p.recv_flag + blk.pkt)) >> 32) != p.epoch)
+                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, blk.pkt, (unsigned int)(f >> 32), p.epoch);
+                }
+                const int cnt = (int)(f & 0xffffffffull);
+                if (mblk == 0 && nt == 0 && blk.kind == 0) p.recv_cnt[blk.pkt] = cnt;
+                if (mblk * BLOCK_M >= cnt) continue;  // empty row block of the static superset
+                if (blk.kind == 1) {  // GEMM1 needs the whole h row block (reference notifyNext, processor.cuh:490-615)
+                    SpinGuard g;
+                    const unsigned int* ctr = p.g0_done + (size_t)blk.pkt * p.TCM + mblk;
+                    while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
+                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, blk.pkt, mblk, 0);
+                }
+                ti.kind = blk.kind; ti.pkt = blk.pkt; ti.mblk = mblk; ti.ntile = nt;
+                ti.rows = min(BLOCK_M, cnt - mblk * BLOCK_M);
+                ti.src = src; ti.le = le;
+                break;
+            }
+            mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
+            ring[q] = ti;
+            mbar_arrive(&sched_full[q]);
+            kind = ti.kind;
+            if (kind >= 0) {
+                a_row = ti.pkt * p.pEC + ti.mblk * BLOCK_M;
+                // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
+                // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
+                b_row = (kind == 0 ? ti.le * 2 * p.P : (ti.le * 2 + 1) * p.H) + ti.ntile * BLOCK_N;
+                nk = (kind == 0 ? p.H : p.P) / BLOCK_K;
+            }
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        if (++q == NSCHED) { q = 0; qphase ^= 1; }
+        if (kind < 0) break;
+        if (lane == 0) {
+            fence_proxy_async_global();  // rows written by generic-proxy stores (peers / other SMs) -> TMA reads
+            const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
+            const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
+                mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                uint8_t* sa = smem + stage * STAGE_BYTES;
+                tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
+                tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base) {
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* sched_full = bars + 2 * STAGES + 4;
+    uint64_t* sched_empty = sched_full + NSCHED;
+    const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+    int stage = 0, phase = 0, q = 0, qphase = 0, as = 0, aphase = 0;
+    for (;;) {
+        int kind = -1;
+        if (lane == 0) {
+            mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, q);
+            kind = ring[q].kind;
+            mbar_arrive(&sched_empty[q]);
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        if (++q == NSCHED) { q = 0; qphase ^= 1; }
+        if (kind < 0) break;
+        const int nk = (kind == 0 ? p.H : p.P) / BLOCK_K;
+        if (lane == 0) {
+            mbar_wait(&tmem_empty[as], aphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_EMPTY, as);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)as * BLOCK_N;
+            for (int kb = 0; kb < nk; ++kb) {
+                mbar_wait(&full[stage], phase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, stage);
+                tcgen05_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint64_t da = umma_smem_desc_sw128(sa);
+                const uint64_t db = umma_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                    // +32 bytes per UMMA_K step inside the 128-byte swizzle row (address field is in 16-byte units)
+                    umma_bf16_ss(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                                 (kb | kk) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&tmem_full[as]);     // accumulator complete -> epilogue
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == 0) return fmaxf(v, 0.0f);                                   // ReLU  (types.cuh:151-159)
+    return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));             // GELU, erf form
+}
+
+__device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base) {
+    uint64_t* tmem_full = bars + 2 * STAGES;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint64_t* sched_full = bars + 2 * STAGES + 4;
+    uint64_t* sched_empty = sched_full + NSCHED;
+    const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
+    uint8_t* stg = smem + OFF_EPI + quarter * EPI_WARP_BYTES;
+    int q = 0, qphase = 0, as = 0, aphase = 0;
+    for (;;) {
+        mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, 100 + q);
+        const TileInfo ti = ring[q];
+        mbar_arrive(&sched_empty[q]);
+        if (++q == NSCHED) { q = 0; qphase ^= 1; }
+        if (ti.kind < 0) break;
+        const int N = ti.kind == 0 ? p.P : p.H;
+        const int n0 = ti.ntile * BLOCK_N;
+        const __nv_bfloat16* bias = ti.kind == 0 ? (p.b_up ? p.b_up + (size_t)ti.le * p.P : nullptr)
+                                                 : (p.b_down ? p.b_down + (size_t)ti.le * p.H : nullptr);
+        // destination rows: GEMM0 -> local h staging; GEMM1 -> the SOURCE rank's return buffer (peer store),
+        // like the reference's GEMM1 epilogue writing into the peer heap (packet.cuh:338-340, processor.cuh:713-720)
+        __nv_bfloat16* out_rows;
+        if (ti.kind == 0) {
+            out_rows = p.hidden + ((size_t)ti.pkt * p.pEC + (size_t)ti.mblk * BLOCK_M) * p.P;
+        } else {
+            const int e_global = p.rank * p.nLx + ti.le;
+            out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)ti.mblk * BLOCK_M) * p.H;
+        }
+        const int nchunks = min(BLOCK_N / 64, (N - n0) / 64);
+
+        mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
+        tcgen05_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * BLOCK_N;
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t v0[32], v1[32];
+            tmem_ld_32x32b_x32(t_row + c * 64, v0);
+            tmem_ld_32x32b_x32(t_row + c * 64 + 32, v1);
+            tmem_ld_wait();
+            if (c == nchunks - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp
+                tcgen05_fence_before();
+                mbar_arrive(&tmem_empty[as]);
+            }
+            float bv[8];
+            uint8_t* my_row = stg + lane * EPI_ROW_BYTES;
+#pragma unroll
+            for (int g8 = 0; g8 < 8; ++g8) {   // 8 groups of 8 columns -> one 16-byte smem store each
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int col = g8 * 8 + i;
+                    f[i] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+                }
+                if (bias != nullptr) {
+                    unpack8(ld_global_nc_v4(bias + n0 + c * 64 + g8 * 8), bv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] += bv[i];
+                }
+                if (ti.kind == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(my_row + g8 * 16) = o;
+            }
+            __syncwarp();
+            // transposed read-back: 8 lanes cover one row's 128 bytes, 4 rows per instruction, full-line stores
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + (lane >> 3), seg = lane & 7;
+                const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_ROW_BYTES + seg * 16);
+                const int row_in_tile = quarter * 32 + r;
+                if (row_in_tile < ti.rows)
+                    st_global_v4(out_rows + (size_t)row_in_tile * N + n0 + c * 64 + seg * 8, o);
+            }
+            __syncwarp();
+        }
+        if (nchunks <= 0) {  // cannot happen (N % 64 == 0 and n0 < N) but never leave the accumulator unreleased
+            tcgen05_fence_before();
+            mbar_arrive(&tmem_empty[as]);
+        }
+        if (++as == 2) { as = 0; aphase ^= 1; }
+
+        // publish: all 128 epilogue threads' stores -> one counter bump / flag
+        if (ti.kind == 0) fence_proxy_async_global();   // h will be read by TMA (async proxy) on other SMs
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == EPI_WARP0 * 32) {
+            if (ti.kind == 0) {
+                fence_proxy_async_global();
+                red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + ti.mblk, 1u);
+            } else {
+                fence_acq_rel_sys();
+                const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + ti.mblk, 1u);
+                if (old == (unsigned int)p.TN1 - 1u) {  // whole rows of this block are on the source rank
+                    fence_acq_rel_sys();
+                    const int e_global = p.rank * p.nLx + ti.le;
+                    st_release_sys_u64(p.peer_ret_flag[ti.src] + (size_t)e_global * p.TCM + ti.mblk,
+                                       ((unsigned long long)p.epoch << 32) | (unsigned int)ti.rows);
+                }
+            }
+        }
+    }
+}
+
+// ============================================================================================================
+// Phase C: combine.  For token t with picks (e_j, slot_j):
+//   k > 1: out[t,c] = bf16-accumulate over kept j of rne( p~_j * rne( y_j[c] / mCw ) )   (processor.cuh:110-169)
+//   k = 1: out[t,:] = y_0 (no scaling), zeros if dropped                                  (processor.cuh:170-203)
+// Deterministic gather (no atomics, no zero-fill pass); for k == 2 it equals the reference's atomicAdd result
+// exactly because bf16 addition commutes and 0 + a is exact.
+// ============================================================================================================
+__device__ __forceinline__ void combine_phase(const FmParams& p, int t0, int n_tok) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = p.H, k = p.k;
+    for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
+        const int t = t0 + ti;
+        const __nv_bfloat16* yrow[8];
+        float pw[8];
+        bool keep[8];
+        const float mcw = p.mcw[t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            keep[j] = false;
+            yrow[j] = nullptr;
+            pw[j] = 0.0f;
+            if (j < k) {
+                const int e = p.topk_idx[(size_t)t * k + j];
+                const int s = p.slot[(size_t)t * k + j];
+                pw[j] = __bfloat162float(p.topk_w[(size_t)t * k + j]);
+                keep[j] = s < p.EC;
+                if (keep[j]) {
+                    const unsigned long long* fl = p.ret_flag + (size_t)e * p.TCM + (s / BLOCK_M);
+                    SpinGuard g;
+                    while ((ld_acquire_sys_u64(fl) >> 32) != p.epoch)
+                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_RET_FLAG, e, s, t);
+                    yrow[j] = p.ret_y + ((size_t)e * p.pEC + s) * H;
+                }
+            }
+        }
+        __nv_bfloat16* orow = p.out + (size_t)t * H;
+        for (int h = lane * 8; h < H; h += 256) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+            if (k == 1) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (keep[0]) v = ld_global_v4(yrow[0] + h);
+                st_global_v4(orow + h, v);
+                continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (j < k && keep[j]) {
+                    float y[8];
+                    unpack8(ld_global_v4(yrow[j] + h), y);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float qv = rne_bf16(__fdividef(y[i], mcw));
+                        const float term = rne_bf16(pw[j] * qv);
+                        acc[i] = rne_bf16(acc[i] + term);
+                    }
+                }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+            o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+            st_global_v4(orow + h, o);
+        }
+    }
+}
+
+// ============================================================================================================
+__global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __grid_constant__ FmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int t0 = blockIdx.x * p.tpc;
+    const int n_tok = max(0, min(p.tpc, p.S - t0));
+
+    // per-launch reset of the work counters (reference clearState, moe.cuh:21-70); consumed only after the grid barrier
+    if (p.phase_mask & 1u) {
+        if (blockIdx.x == 0) {
+            for (int i = tid; i < p.num_pkts * p.TCM; i += NUM_THREADS) {
+                p.g0_done[i] = 0u;
+                p.g1_done[i] = 0u;
+            }
+            if (tid == 0) {
+                *p.claim = 0u;
+                *p.disp_done = 0u;
+            }
+        }
+        gate_phase(p, smem, t0, n_tok);
+        grid_barrier(p);
+        dispatch_phase(p, smem, t0, n_tok);
+    } else if (blockIdx.x == 0 && tid == 0) {
+        *p.claim = 0u;   // debug re-run of later phases on the previous routing
+    }
+    __syncthreads();
+
+    if (p.phase_mask & 2u) {
+        if (warp == 1 && (tid & 31) == 0) {
+            uint64_t* full = bars;
+            uint64_t* empty = bars + STAGES;
+            uint64_t* tmem_full = bars + 2 * STAGES;
+            uint64_t* tmem_empty = tmem_full + 2;
+            uint64_t* sched_full = bars + 2 * STAGES + 4;
+            uint64_t* sched_empty = sched_full + NSCHED;
+            for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+            for (int i = 0; i < NSCHED; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 129); }
+            fence_mbar_init();
+        }
+        if (warp == 0 && (tid & 31) == 0) {
+            tma_prefetch_desc(&p.tm_a0); tma_prefetch_desc(&p.tm_b0);
+            tma_prefetch_desc(&p.tm_a1); tma_prefetch_desc(&p.tm_b1);
+        }
+        if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+        tcgen05_fence_before();
+        __syncthreads();
+        tcgen05_fence_after();
+        const uint32_t tmem_base = *tmem_ptr;
+
+        if (warp == 0) ffn_producer(p, smem, bars);
+        else if (warp == 1) ffn_mma(p, smem, bars, tmem_base);
+        else if (warp >= EPI_WARP0) ffn_epilogue(p, smem, bars, tmem_base);
+
+        tcgen05_fence_before();
+        __syncthreads();
+        if (warp == 2) {
+            tcgen05_fence_after();
+            tmem_dealloc(tmem_base, TMEM_COLS);
+        }
+    }
+    if (p.phase_mask & 4u) combine_phase(p, t0, n_tok);
+}
+
+}  // namespace fm

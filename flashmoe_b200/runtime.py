@@ -1,0 +1,221 @@
+"""Host-side runtime above the C-ABI: one `MoEContext` per process / GPU.
+
+Mirrors what the reference does in `flashmoe::initialize()` + `moe_forward` (csrc/include/flashmoe/bootstrap.cuh:278-547,
+csrc/python_bindings.cu:17-151) with torch used only for device memory, streams and the out-of-band exchange of
+CUDA IPC handles (`torch.distributed`, any backend) -- plumbing, not the product.  All math runs in the native
+library; nothing here falls back to torch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import MoEConfig
+
+_BUFFER_SPECS = {
+    "topk_idx": (_lib.BUF_TOPK_IDX, np.int32),
+    "topk_w": (_lib.BUF_TOPK_W, np.uint16),
+    "mcw": (_lib.BUF_MCW, np.float32),
+    "slot": (_lib.BUF_SLOT, np.int32),
+    "counts": (_lib.BUF_COUNTS, np.int32),
+    "recv_x": (_lib.BUF_RECV_X, np.uint16),
+    "hidden": (_lib.BUF_HIDDEN, np.uint16),
+    "ret_y": (_lib.BUF_RET_Y, np.uint16),
+    "gate_out": (_lib.BUF_GATE_OUT, np.uint16),
+    "recv_cnt": (_lib.BUF_RECV_CNT, np.int32),
+}
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    """(rank, world, local_rank) from torchrun's env, falling back to the launchers the reference's worker reads
+    (OMPI / PMI / SLURM, reference flashmoe/worker.py:24-29)."""
+    def first(*names: str, default: str) -> int:
+        for n in names:
+            if n in os.environ:
+                return int(os.environ[n])
+        return int(default)
+
+    rank = first("RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID", default="0")
+    world = first("WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", default="1")
+    local = first("LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", default=str(rank))
+    return rank, world, local
+
+
+def _check_tensor(name: str, t: torch.Tensor, device: torch.device) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be CUDA tensor")
+    if t.device != device:
+        raise RuntimeError(f"{name} is on {t.device}, context is on {device}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != torch.bfloat16:
+        raise RuntimeError(f"{name} must be torch.bfloat16 (compiled Element), got {t.dtype}")
+
+
+class MoEContext:
+    """Owns the native context (workspaces, symmetric slab, peer mappings) for one rank."""
+
+    def __init__(self, cfg: Optional[MoEConfig] = None, rank: int = 0, world: int = 1,
+                 device: Optional[int] = None, group=None, timeout_ms: Optional[int] = None):
+        self._L = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device)
+        self.rank, self.world = rank, world
+        ccfg = _lib.FmConfig.from_config(cfg) if cfg is not None else None
+        _lib.check(self._L.fm_create(ctypes.byref(ccfg) if ccfg is not None else None, rank, world, device,
+                                     ctypes.byref(self._ctx)))
+        d = _lib.FmDims()
+        _lib.check(self._L.fm_get_dims(self._ctx, ctypes.byref(d)))
+        self.dims: Dict[str, int] = {k: int(getattr(d, k)) for k, _ in d._fields_}
+        self.cfg = cfg if cfg is not None else _lib.compiled_config()
+        if timeout_ms is not None:
+            _lib.check(self._L.fm_set_timeout_ms(self._ctx, int(timeout_ms)))
+        if world > 1:
+            self._attach_peers(group)
+
+    # ------------------------------------------------------------------ peers
+    def _attach_peers(self, group) -> None:
+        """Exchange CUDA IPC handles of the symmetric slab over torch.distributed and map every peer
+        (replaces nvshmem_malloc + nvshmem_ptr, reference bootstrap.cuh:359-360,442-443)."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("world > 1 needs an initialised torch.distributed process group")
+        handle = (ctypes.c_ubyte * _lib.FM_IPC_HANDLE_BYTES)()
+        _lib.check(self._L.fm_symm_export(self._ctx, handle))
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, bytes(handle), group=group)
+        blob = b"".join(gathered)
+        assert len(blob) == self.world * _lib.FM_IPC_HANDLE_BYTES
+        _lib.check(self._L.fm_symm_attach_ipc(self._ctx, blob))
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)  # every rank's slab is mapped (and zeroed) before anyone dispatches into it
+
+    # ------------------------------------------------------------------ hot path
+    @property
+    def num_local_experts(self) -> int:
+        return self.dims["num_local_experts"]
+
+    def _validate(self, input: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor) -> None:
+        """Same conditions as the reference's TORCH_CHECKs (python_bindings.cu:22-65) plus a dtype check."""
+        d = self.dims
+        _check_tensor("Input", input, self.device)
+        _check_tensor("Gate weights", gate_weights, self.device)
+        _check_tensor("Expert weights", expert_weights, self.device)
+        if input.dim() != 3:
+            raise RuntimeError("Input must be 3D [batch, seq, H]")
+        if input.size(0) * input.size(1) != d["S"]:
+            raise RuntimeError(f"Input batch*seq must equal compiled S={d['S']}. Got batch={input.size(0)}, "
+                               f"seq={input.size(1)} (product={input.size(0) * input.size(1)})")
+        if input.size(2) != d["H"]:
+            raise RuntimeError(f"Input hidden_size must equal compiled H={d['H']}. Got {input.size(2)}")
+        if gate_weights.dim() != 2 or gate_weights.size(0) != d["H"] or gate_weights.size(1) != d["E"]:
+            raise RuntimeError(f"Gate weights must be [H={d['H']}, E={d['E']}]. Got {list(gate_weights.shape)}")
+        nlx = d["num_local_experts"]
+        if expert_weights.dim() != 4 or expert_weights.size(0) != nlx:
+            raise RuntimeError(f"Expert count mismatch. Expected {nlx} local experts, got {expert_weights.size(0)}")
+        if expert_weights.size(1) != 2:
+            raise RuntimeError("Expert weights must have up and down projections [nLx, 2, P, H]")
+        if expert_weights.size(2) != d["P"] or expert_weights.size(3) != d["H"]:
+            raise RuntimeError(f"Expert weights must be [*, 2, P={d['P']}, H={d['H']}]. Got [*, 2, "
+                               f"{expert_weights.size(2)}, {expert_weights.size(3)}]")
+
+    def _bias_ptrs(self, bias_up, bias_down):
+        d = self.dims
+        nlx = d["num_local_experts"]
+        for name, b, n in (("bias_up", bias_up, d["P"]), ("bias_down", bias_down, d["H"])):
+            if b is not None:
+                _check_tensor(name, b, self.device)
+                if tuple(b.shape) != (nlx, n):
+                    raise RuntimeError(f"{name} must be [{nlx}, {n}], got {list(b.shape)}")
+        return (bias_up.data_ptr() if bias_up is not None else None,
+                bias_down.data_ptr() if bias_down is not None else None)
+
+    def forward(self, input: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor,
+                bias_up: Optional[torch.Tensor] = None, bias_down: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None, phase_mask: int = 7) -> torch.Tensor:
+        """Enqueue one fused forward on torch's current stream; returns the [B,T,H] output tensor (async)."""
+        self._validate(input, gate_weights, expert_weights)
+        bu, bd = self._bias_ptrs(bias_up, bias_down)
+        if out is None:
+            out = torch.empty_like(input)
+        else:
+            _check_tensor("out", out, self.device)
+            if out.shape != input.shape:
+                raise RuntimeError("out must have the input's shape")
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if phase_mask == 7:
+            rc = self._L.fm_moe_forward(self._ctx, input.data_ptr(), gate_weights.data_ptr(),
+                                        expert_weights.data_ptr(), bu, bd, out.data_ptr(), stream)
+        else:
+            rc = self._L.fm_debug_forward(self._ctx, input.data_ptr(), gate_weights.data_ptr(),
+                                          expert_weights.data_ptr(), bu, bd, out.data_ptr(), stream, phase_mask)
+        _lib.check(rc)
+        return out
+
+    def forward_host(self, input_host: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor,
+                     out_host: Optional[torch.Tensor] = None, bias_up: Optional[torch.Tensor] = None,
+                     bias_down: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end call with HOST activations (pinned for full PCIe rate): H2D copy, fused forward, D2H copy,
+        stream synchronise.  Weights stay device-resident (they are parameters, not per-step inputs)."""
+        d = self.dims
+        if input_host.is_cuda or input_host.dtype != torch.bfloat16 or not input_host.is_contiguous():
+            raise RuntimeError("input_host must be a contiguous CPU torch.bfloat16 tensor")
+        if input_host.numel() != d["S"] * d["H"]:
+            raise RuntimeError(f"input_host must hold S*H = {d['S'] * d['H']} elements")
+        _check_tensor("Gate weights", gate_weights, self.device)
+        _check_tensor("Expert weights", expert_weights, self.device)
+        bu, bd = self._bias_ptrs(bias_up, bias_down)
+        if out_host is None:
+            out_host = torch.empty_like(input_host, pin_memory=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._L.fm_moe_forward_host(self._ctx, input_host.data_ptr(), gate_weights.data_ptr(),
+                                               expert_weights.data_ptr(), bu, bd, out_host.data_ptr(), stream))
+        return out_host
+
+    def check(self) -> None:
+        """Raise if the last kernel reported a protocol timeout (call after a synchronise)."""
+        _lib.check(self._L.fm_check(self._ctx))
+
+    def synchronize(self) -> None:
+        try:
+            torch.cuda.synchronize(self.device)
+        finally:
+            self.check()
+
+    def read(self, name: str) -> np.ndarray:
+        """Copy an internal buffer (routing tables, staging areas) to host -- tests and debugging only."""
+        which, dt = _BUFFER_SPECS[name]
+        nbytes = ctypes.c_size_t()
+        _lib.check(self._L.fm_buffer_bytes(self._ctx, which, ctypes.byref(nbytes)))
+        arr = np.empty(nbytes.value // np.dtype(dt).itemsize, dtype=dt)
+        _lib.check(self._L.fm_read_buffer(self._ctx, which, arr.ctypes.data_as(ctypes.c_void_p), nbytes.value))
+        d = self.dims
+        k, E, S, H, P = d["k"], d["E"], d["S"], d["H"], d["P"]
+        npk = d["world"] * d["num_local_experts"]
+        shapes = {"topk_idx": (S, k), "topk_w": (S, k), "mcw": (S,), "slot": (S, k), "counts": (E,),
+                  "recv_x": (npk, d["pEC"], H), "hidden": (npk, d["pEC"], P), "ret_y": (E, d["pEC"], H),
+                  "gate_out": (S, E), "recv_cnt": (npk,)}
+        return arr.reshape(shapes[name])
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.fm_launch_count(self._ctx))
+
+    def close(self) -> None:
+        if self._ctx:
+            self._L.fm_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
