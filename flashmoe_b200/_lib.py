@@ -15,13 +15,14 @@ FM_MAX_WORLD = 16
 FM_IPC_HANDLE_BYTES = 64
 
 # enum fm_buffer
-BUF_TOPK_IDX, BUF_TOPK_W, BUF_MCW, BUF_SLOT, BUF_COUNTS, BUF_RECV_X, BUF_HIDDEN, BUF_RET_Y, BUF_GATE_OUT, BUF_RECV_CNT = range(10)
+BUF_TOPK_IDX, BUF_TOPK_W, BUF_MCW, BUF_SLOT, BUF_COUNTS, BUF_RECV_X, BUF_HIDDEN, BUF_RET_Y, BUF_GATE_OUT, BUF_RECV_CNT, BUF_TRACE = range(11)
 
 # every symbol include/flashmoe_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
     "fm_compiled_config", "fm_create", "fm_destroy", "fm_get_dims", "fm_num_local_experts", "fm_symm_size",
     "fm_symm_local_ptr", "fm_symm_export", "fm_symm_attach_ipc", "fm_symm_attach_ptrs", "fm_symm_use_external",
-    "fm_moe_forward", "fm_moe_forward_host", "fm_check", "fm_set_timeout_ms", "fm_launch_count", "fm_buffer_bytes",
+    "fm_moe_forward", "fm_moe_forward_host", "fm_check", "fm_set_timeout_ms", "fm_set_trace", "fm_launch_count",
+    "fm_buffer_bytes",
     "fm_read_buffer", "fm_debug_forward", "fm_last_error", "fm_version",
 )
 
@@ -75,6 +76,7 @@ def load() -> ctypes.CDLL:
     L.fm_debug_forward.argtypes = [vp, cvp, cvp, cvp, cvp, cvp, vp, vp, ctypes.c_uint32]
     L.fm_check.argtypes = [vp]
     L.fm_set_timeout_ms.argtypes = [vp, ctypes.c_uint32]
+    L.fm_set_trace.argtypes = [vp, ctypes.c_int]
     L.fm_launch_count.argtypes = [vp]
     L.fm_launch_count.restype = ctypes.c_uint64
     L.fm_buffer_bytes.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]

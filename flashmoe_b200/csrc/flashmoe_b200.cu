@@ -9,6 +9,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -101,6 +102,7 @@ struct fm_ctx {
     int grid = 0;
     int tpc = 0;
     int TN0 = 0, TN1 = 0, num_pkts = 0, num_blocks = 0, total_items = 0;
+    int bn0 = 256, bn1 = 256, claim_ahead_kb = 8;
     uint32_t epoch = 0;
     unsigned long long bar_count = 0;
     unsigned long long timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
@@ -130,6 +132,8 @@ struct fm_ctx {
     bool attached = false;
     fm::DebugRecord* dbg_host = nullptr;
     fm::DebugRecord* dbg_dev = nullptr;
+    unsigned long long* trace = nullptr;
+    bool trace_on = false;
     // tensor-map cache (re-encoded only when the caller's weight pointer changes)
     const void* cached_expert_w = nullptr;
     CUtensorMap tm_a0, tm_b0, tm_a1, tm_b1;
@@ -238,8 +242,8 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
         // (python_bindings.cu:104-119).  One tensor map per GEMM over the whole tensor with a per-expert row stride
         // of 2*P (resp. 2*H) rows is not expressible in 2-D, so rows are addressed as [nLx*2*P, H] / [nLx*2*H, P]:
         // expert i's W_up starts at row i*2*P, its W_down at row (i*2+1)*H of the [.,P] view.
-        if ((rc = make_tmap(&c->tm_b0, expert_w, (uint64_t)nLx * 2 * d.P, d.H, fm::BLOCK_N))) return rc;
-        if ((rc = make_tmap(&c->tm_b1, expert_w, (uint64_t)nLx * 2 * d.H, d.P, fm::BLOCK_N))) return rc;
+        if ((rc = make_tmap(&c->tm_b0, expert_w, (uint64_t)nLx * 2 * d.P, d.H, (uint32_t)c->bn0))) return rc;
+        if ((rc = make_tmap(&c->tm_b1, expert_w, (uint64_t)nLx * 2 * d.H, d.P, (uint32_t)c->bn1))) return rc;
         c->cached_expert_w = expert_w;
     }
     fm::FmParams p;
@@ -249,6 +253,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.EC = d.EC; p.pEC = d.pEC; p.TCM = d.TCM; p.act = c->cfg.hidden_act;
     p.TN0 = c->TN0; p.TN1 = c->TN1; p.tpc = c->tpc; p.num_pkts = c->num_pkts; p.num_blocks = c->num_blocks;
     p.total_items = c->total_items;
+    p.bn[0] = c->bn0; p.bn[1] = c->bn1; p.claim_ahead_kb = c->claim_ahead_kb;
     if (phase_mask & 1u) {
         c->epoch += 1;
         c->bar_count += (unsigned long long)c->grid;
@@ -275,6 +280,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.ret_flag = reinterpret_cast<unsigned long long*>(sb + c->off_ret_flag);
     set_peer_pointers(c, p);
     p.dbg = c->dbg_dev;
+    p.trace = c->trace_on ? c->trace : nullptr;
 
     void* args[] = {&p};
     FM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel), dim3(c->grid),
@@ -357,8 +363,17 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         return fail(FM_EINVAL, "tokens-per-CTA * k = %d exceeds the router scratch (%d)", ctx->tpc * d.k, fm::G_SEL_MAX);
     }
     const int nLx = d.num_local_experts;
-    ctx->TN0 = ceil_div(d.P, fm::BLOCK_N);
-    ctx->TN1 = ceil_div(d.H, fm::BLOCK_N);
+    // tuning knobs (tile widths of the two GEMMs, scheduler look-ahead); environment overrides are for experiments
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return (v != nullptr && *v) ? atoi(v) : dflt;
+    };
+    ctx->bn0 = env_int("FM_BN0", 256) == 128 ? 128 : 256;
+    ctx->bn1 = env_int("FM_BN1", 256) == 128 ? 128 : 256;
+    ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 8);
+    if (ctx->claim_ahead_kb < 0) ctx->claim_ahead_kb = 0;
+    ctx->TN0 = ceil_div(d.P, ctx->bn0);
+    ctx->TN1 = ceil_div(d.H, ctx->bn1);
     ctx->num_pkts = world * nLx;
 
     // work-item blocks: own rank's packets first, then rank+1, ...; GEMM1 lags GEMM0 by one packet
@@ -417,6 +432,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     FM_TRY(dev_alloc(&ctx->blocks, blocks.size(), false));
     FM_TRY_CUDA(cudaMemcpy(ctx->blocks, blocks.data(), blocks.size() * sizeof(fm::TileBlock), cudaMemcpyHostToDevice));
     FM_TRY(dev_alloc(&ctx->hidden, (size_t)ctx->num_pkts * d.pEC * d.P));
+    FM_TRY(dev_alloc(&ctx->trace, (size_t)ctx->grid * fm::TRACE_SLOTS));
 
     // symmetric slab: [recv_x | ret_y | recv_flag | ret_flag]  (reference heap + flags, bootstrap.cuh:348-362)
     size_t off = 0;
@@ -456,7 +472,7 @@ FM_API int fm_destroy(fm_ctx_t* ctx) {
     for (int r = 0; r < ctx->d.world; ++r)
         if (ctx->peer_opened[r] && ctx->peer_base[r] != nullptr) cudaIpcCloseMemHandle(ctx->peer_base[r]);
     void* bufs[] = {ctx->topk_idx, ctx->topk_w, ctx->mcw, ctx->slot, ctx->counts, ctx->gate_out, ctx->chunk_counts,
-                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->x_stage,
+                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace, ctx->x_stage,
                     ctx->out_stage};
     for (void* b : bufs)
         if (b != nullptr) cudaFree(b);
@@ -584,6 +600,12 @@ FM_API int fm_set_timeout_ms(fm_ctx_t* ctx, uint32_t ms) {
     return FM_OK;
 }
 
+FM_API int fm_set_trace(fm_ctx_t* ctx, int enable) {
+    if (ctx == nullptr) return fail(FM_EINVAL, "null context");
+    ctx->trace_on = enable != 0;
+    return FM_OK;
+}
+
 FM_API uint64_t fm_launch_count(const fm_ctx_t* ctx) { return ctx ? ctx->launches : 0; }
 
 static int buffer_desc(const fm_ctx_t* c, int which, const void** ptr, size_t* bytes) {
@@ -600,6 +622,7 @@ static int buffer_desc(const fm_ctx_t* c, int which, const void** ptr, size_t* b
         case FM_BUF_RET_Y: *ptr = sb + c->off_ret_y; *bytes = (size_t)d.E * d.pEC * d.H * 2; break;
         case FM_BUF_GATE_OUT: *ptr = c->gate_out; *bytes = (size_t)d.S * d.E * 2; break;
         case FM_BUF_RECV_CNT: *ptr = c->recv_cnt; *bytes = (size_t)c->num_pkts * 4; break;
+        case FM_BUF_TRACE: *ptr = c->trace; *bytes = (size_t)c->grid * fm::TRACE_SLOTS * 8; break;
         default: return fail(FM_EINVAL, "unknown buffer id %d", which);
     }
     return FM_OK;

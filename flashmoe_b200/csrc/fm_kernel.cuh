@@ -27,7 +27,7 @@
 namespace fm {
 
 constexpr int BLOCK_M = 128;   // token rows per tile (= reference BLOCK_M)
-constexpr int BLOCK_N = 256;   // output columns per tile (one tcgen05.mma N)
+constexpr int BLOCK_N = 256;   // max output columns per tile (one tcgen05.mma N); per-GEMM width is p.bn[kind]
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
@@ -36,6 +36,7 @@ constexpr int NUM_THREADS = 256;
 constexpr int NUM_WARPS = NUM_THREADS / 32;
 constexpr int EPI_WARP0 = 4;   // warps 4..7 (warp % 4 selects the TMEM lane quarter)
 constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators
+constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [7] tiles, [16+i] tile i ready, [64+i] tile i stored
 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                  // 16 KiB
 constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;                  // 32 KiB
@@ -44,10 +45,10 @@ constexpr int EPI_ROW_BYTES = 144;                                    // 128 B o
 constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
 constexpr int OFF_EPI = STAGES * STAGE_BYTES;                         // 196608
 constexpr int OFF_BARS = OFF_EPI + 4 * EPI_WARP_BYTES;                // 215040
-constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * NSCHED;                 // 20
-constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 215200
-constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 32;                  // 215328
-constexpr int OFF_MISC = OFF_TMEM_PTR + 16;                           // 215344
+constexpr int NUM_BARS = 2 * STAGES + 4 + 3 * NSCHED;                 // 24
+constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 215232
+constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 48;
+constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
 constexpr int SMEM_USED = OFF_MISC + 64;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                          // + slack for manual 1 KiB alignment
 
@@ -75,6 +76,8 @@ struct FmParams {
     CUtensorMap tm_b1;  // expert_weights as [nLx*2*H, P]  box {64, 256}  (W_down rows)
     int S, H, P, E, k, W, rank, nLx, EC, pEC, TCM, act;
     int TN0, TN1, tpc, num_pkts, num_blocks, total_items;
+    int bn[2];          // tile width of GEMM0 / GEMM1 (128 or 256)
+    int claim_ahead_kb; // the scheduler claims the next tile when this many k-blocks of the current one remain
     unsigned int epoch, phase_mask;
     unsigned long long bar_target, timeout_ns;
     const __nv_bfloat16 *x, *wg, *b_up, *b_down;
@@ -103,9 +106,15 @@ struct FmParams {
     __nv_bfloat16* peer_ret_y[FM_MAX_WORLD];
     unsigned long long* peer_ret_flag[FM_MAX_WORLD];
     DebugRecord* dbg;
+    unsigned long long* trace;  // optional [grid][TRACE_SLOTS] %globaltimer stamps (nullptr = off)
 };
 
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void trace_stamp(const FmParams& p, int slot) {
+    if (p.trace != nullptr && slot < TRACE_SLOTS)
+        p.trace[(size_t)blockIdx.x * TRACE_SLOTS + slot] = globaltimer_ns();
+}
+
 __device__ __forceinline__ void grid_barrier(const FmParams& p) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -178,32 +187,66 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                     *reinterpret_cast<uint4*>(wg_s + (size_t)e * Hc + v * 8) = w;
                 }
                 __syncthreads();
-                for (int ti = warp; ti < n_sub; ti += NUM_WARPS) {
-                    const __nv_bfloat16* xr = p.x + (size_t)(t0 + s0 + ti) * H + hc0;
-                    for (int sub = 0; sub * 32 < eg_len; ++sub) {
-                        const int ne = min(32, eg_len - sub * 32);
+                // register-blocked GEMV: a warp takes 4 tokens x 8 experts at a time (32 accumulators per lane, one per
+                // (token, expert) pair), lanes split the H columns in 16-byte pieces; all of a step's global loads are
+                // issued before the first FMA, and each staged Wg piece is reused by the 4 tokens.
+                for (int tb = warp * 4; tb < n_sub; tb += NUM_WARPS * 4) {
+                    const int ntk = min(4, n_sub - tb);
+                    const __nv_bfloat16* xr = p.x + (size_t)(t0 + s0 + tb) * H + hc0;
+                    const bool single = hc_len <= 1024;
+                    uint4 xv[4][4];
+                    if (single) {
+#pragma unroll
+                        for (int tk = 0; tk < 4; ++tk)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int h = i * 256 + lane * 8;
+                                xv[tk][i] = (tk < ntk && h < hc_len) ? ld_global_nc_v4(xr + (size_t)tk * H + h)
+                                                                     : make_uint4(0u, 0u, 0u, 0u);
+                            }
+                    }
+                    for (int g8 = 0; g8 * 8 < eg_len; ++g8) {
+                        const int ne = min(8, eg_len - g8 * 8);
                         float acc[32];
 #pragma unroll
                         for (int e = 0; e < 32; ++e) acc[e] = 0.0f;
-                        for (int p0 = 0; p0 < hc_len; p0 += 256) {
-                            const int h = p0 + lane * 8;
-                            if (h < hc_len) {
-                                float xf[8];
-                                unpack8(ld_global_nc_v4(xr + h), xf);
-                                const __nv_bfloat16* wrow = wg_s + (size_t)(sub * 32) * Hc + h;
+                        for (int pg = 0; pg < hc_len; pg += 1024) {
+                            if (!single) {
 #pragma unroll
-                                for (int e = 0; e < 32; ++e) {
-                                    if (e < ne) {
-                                        float wf[8];
-                                        unpack8(*reinterpret_cast<const uint4*>(wrow + (size_t)e * Hc), wf);
+                                for (int tk = 0; tk < 4; ++tk)
 #pragma unroll
-                                        for (int q = 0; q < 8; ++q) acc[e] = fmaf(xf[q], wf[q], acc[e]);
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int h = pg + i * 256 + lane * 8;
+                                        xv[tk][i] = (tk < ntk && h < hc_len) ? ld_global_nc_v4(xr + (size_t)tk * H + h)
+                                                                             : make_uint4(0u, 0u, 0u, 0u);
+                                    }
+                            }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int h = pg + i * 256 + lane * 8;
+                                if (h < hc_len) {
+                                    const __nv_bfloat16* wrow = wg_s + (size_t)(g8 * 8) * Hc + h;
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        if (e < ne) {
+                                            float wf[8];
+                                            unpack8(*reinterpret_cast<const uint4*>(wrow + (size_t)e * Hc), wf);
+#pragma unroll
+                                            for (int tk = 0; tk < 4; ++tk) {
+                                                float xf[8];
+                                                unpack8(xv[tk][i], xf);
+#pragma unroll
+                                                for (int q = 0; q < 8; ++q)
+                                                    acc[tk * 8 + e] = fmaf(xf[q], wf[q], acc[tk * 8 + e]);
+                                            }
+                                        }
                                     }
                                 }
                             }
                         }
-                        const float tot = warp_transpose_reduce(acc, lane);
-                        if (lane < ne) logit_s[ti * ldl + eg0 + sub * 32 + lane] += tot;
+                        const float tot = warp_transpose_reduce(acc, lane);   // lane -> (token lane/8, expert lane%8)
+                        const int tk = lane >> 3, e = lane & 7;
+                        if (tk < ntk && e < ne) logit_s[(tb + tk) * ldl + eg0 + g8 * 8 + e] += tot;
                     }
                 }
             }
@@ -276,10 +319,19 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     int* base_s = reinterpret_cast<int*>(smem + G_OFF_BASE);
     unsigned int* misc = reinterpret_cast<unsigned int*>(smem + OFF_MISC);
 
-    for (int e = tid; e < E; e += NUM_THREADS) {
-        int b = 0;
-        for (int c = 0; c < (int)blockIdx.x; ++c) b += p.chunk_counts[(size_t)c * E + e];
-        base_s[e] = b;
+    // base[e] = selections of e by lower chunks: all 256 threads sum the [blockIdx.x, E] prefix of chunk_counts
+    for (int e = tid; e < E; e += NUM_THREADS) base_s[e] = 0;
+    __syncthreads();
+    {
+        const int n = (int)blockIdx.x * E;
+        int part = 0, cur_e = -1;
+        for (int i = tid; i < n; i += NUM_THREADS) {
+            const int e = i % E;
+            const int v = p.chunk_counts[i];
+            if (E <= NUM_THREADS && (NUM_THREADS % E) == 0) { part += v; cur_e = e; }   // a thread always sees one e
+            else atomicAdd(&base_s[e], v);
+        }
+        if (cur_e >= 0 && part != 0) atomicAdd(&base_s[cur_e], part);
     }
     __syncthreads();
     for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
@@ -300,11 +352,22 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             }
         }
         const __nv_bfloat16* src = p.x + (size_t)t * H;
-        for (int h = lane * 8; h < H; h += 256) {
-            const uint4 v = ld_global_nc_v4(src + h);
+        for (int hg = 0; hg < H; hg += 1024) {
+            uint4 v[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < k && keep[j]) st_global_v4(dst[j] + h, v);
+            for (int i = 0; i < 4; ++i) {
+                const int h = hg + i * 256 + lane * 8;
+                if (h < H) v[i] = ld_global_nc_v4(src + h);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int h = hg + i * 256 + lane * 8;
+                if (h < H) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < k && keep[j]) st_global_v4(dst[j] + h, v[i]);
+                }
+            }
         }
     }
     __syncthreads();
@@ -316,9 +379,15 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     }
     __syncthreads();
     if (misc[0]) {  // last CTA: every chunk's rows are out; publish counts to the owners
+        for (int e = tid; e < E; e += NUM_THREADS) base_s[e] = 0;
+        __syncthreads();
+        for (int i = tid; i < G * E; i += NUM_THREADS) {
+            const int v = p.chunk_counts[i];
+            if (v != 0) atomicAdd(&base_s[i % E], v);
+        }
+        __syncthreads();
         for (int e = tid; e < E; e += NUM_THREADS) {
-            int tot = 0;
-            for (int c = 0; c < G; ++c) tot += p.chunk_counts[(size_t)c * E + e];
+            const int tot = base_s[e];
             p.counts[e] = tot;
             const int rows = tot < p.EC ? tot : p.EC;
             const int owner = e / p.nLx, le = e - owner * p.nLx;
@@ -334,7 +403,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
 //   j-1 (one packet of lag so the h row-block a GEMM1 tile needs is normally complete when it is claimed).
 //   item -> (row block m fastest, column tile n).  A GEMM1 tile waits for g0_done[pkt][m] == TN0.
 // ============================================================================================================
-struct TileInfo {     // 32 bytes, written by the claimer, read by the MMA and epilogue warps
+struct TileInfo {     // 48 bytes, written by the scheduler warp, read by the producer, MMA and epilogue warps
     int kind;         // 0 GEMM0, 1 GEMM1, -1 stop
     int pkt;          // local packet index src * nLx + le
     int mblk;
@@ -342,22 +411,33 @@ struct TileInfo {     // 32 bytes, written by the claimer, read by the MMA and e
     int rows;         // valid rows in this row block
     int src;
     int le;
+    int bn;           // tile width
+    int nk;           // k-blocks
+    int a_row;        // TMA row coordinate of the A tile
+    int b_row;        // TMA row coordinate of the B tile
     int pad;
 };
 
-__device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, uint64_t* bars) {
-    uint64_t* full = bars;
-    uint64_t* empty = bars + STAGES;
+// warp 3: claims work items and resolves their dependencies AHEAD of the TMA producer, so the atomic, the packet flag
+// and the h-row-block counter round trips overlap the previous tile's loads (the job of the reference's OS CTA:
+// subscriber decode + scheduler doorbells, os/subscriber.cuh, os/scheduler.cuh -- here one warp per CTA, no queues).
+__device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, uint64_t* bars) {
     uint64_t* sched_full = bars + 2 * STAGES + 4;
     uint64_t* sched_empty = sched_full + NSCHED;
+    uint64_t* prod_take = sched_empty + NSCHED;
     TileInfo* ring = reinterpret_cast<TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
-    int stage = 0, phase = 0, q = 0, qphase = 0, cursor = 0;
+    int q = 0, qphase = 0, cursor = 0, n = 0;
     for (;;) {
-        int kind = -1, nk = 0, a_row = 0, b_row = 0;
+        int kind = -1;
         if (lane == 0) {
+            if (n >= 1) {  // bounded look-ahead: wait until the producer is close to finishing tile n-1
+                const int pq = (q + NSCHED - 1) % NSCHED;
+                mbar_wait(&prod_take[pq], ((n - 1) / NSCHED) & 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, 200 + pq);
+            }
             TileInfo ti;
-            ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows = 0; ti.src = 0; ti.le = 0; ti.pad = 0;
+            ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows = 0; ti.src = 0; ti.le = 0; ti.bn = 0;
+            ti.nk = 0; ti.a_row = 0; ti.b_row = 0; ti.pad = 0;
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
@@ -385,36 +465,65 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
                 ti.kind = blk.kind; ti.pkt = blk.pkt; ti.mblk = mblk; ti.ntile = nt;
                 ti.rows = min(BLOCK_M, cnt - mblk * BLOCK_M);
                 ti.src = src; ti.le = le;
+                ti.bn = p.bn[blk.kind];
+                ti.nk = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
+                ti.a_row = blk.pkt * p.pEC + mblk * BLOCK_M;
+                // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
+                // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
+                ti.b_row = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * ti.bn;
                 break;
             }
+            if (ti.kind >= 0 && n < 48) trace_stamp(p, 16 + n);
             mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
             ring[q] = ti;
             mbar_arrive(&sched_full[q]);
             kind = ti.kind;
-            if (kind >= 0) {
-                a_row = ti.pkt * p.pEC + ti.mblk * BLOCK_M;
-                // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
-                // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
-                b_row = (kind == 0 ? ti.le * 2 * p.P : (ti.le * 2 + 1) * p.H) + ti.ntile * BLOCK_N;
-                nk = (kind == 0 ? p.H : p.P) / BLOCK_K;
-            }
         }
         kind = __shfl_sync(0xffffffffu, kind, 0);
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
+        ++n;
+        if (kind < 0) break;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, uint64_t* bars) {
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* sched_full = bars + 2 * STAGES + 4;
+    uint64_t* sched_empty = sched_full + NSCHED;
+    uint64_t* prod_take = sched_empty + NSCHED;
+    const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
+    const int lane = threadIdx.x & 31;
+    int stage = 0, phase = 0, q = 0, qphase = 0;
+    for (;;) {
+        int kind = -1;
+        TileInfo ti;
+        if (lane == 0) {
+            mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, 300 + q);
+            ti = ring[q];
+            mbar_arrive(&sched_empty[q]);
+            kind = ti.kind;
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
         if (kind < 0) break;
         if (lane == 0) {
             fence_proxy_async_global();  // rows written by generic-proxy stores (peers / other SMs) -> TMA reads
             const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
             const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
-            for (int kb = 0; kb < nk; ++kb) {
+            const uint32_t tx = (uint32_t)(A_STAGE_BYTES + ti.bn * BLOCK_K * 2);
+            const int take_at = max(0, ti.nk - p.claim_ahead_kb);
+            for (int kb = 0; kb < ti.nk; ++kb) {
+                if (kb == take_at) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
-                mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                mbar_arrive_expect_tx(&full[stage], tx);
                 uint8_t* sa = smem + stage * STAGE_BYTES;
-                tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
-                tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
+                tma_load_2d(sa, ta, kb * BLOCK_K, ti.a_row, &full[stage]);
+                tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, ti.b_row, &full[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
+        if (++q == NSCHED) { q = 0; qphase ^= 1; }
         __syncwarp();
     }
 }
@@ -428,20 +537,21 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
     uint64_t* sched_empty = sched_full + NSCHED;
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, BLOCK_N);
     int stage = 0, phase = 0, q = 0, qphase = 0, as = 0, aphase = 0;
     for (;;) {
-        int kind = -1;
+        int kind = -1, nk = 0, bn = BLOCK_N;
         if (lane == 0) {
             mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, q);
             kind = ring[q].kind;
+            nk = ring[q].nk;
+            bn = ring[q].bn;
             mbar_arrive(&sched_empty[q]);
         }
         kind = __shfl_sync(0xffffffffu, kind, 0);
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         if (kind < 0) break;
-        const int nk = (kind == 0 ? p.H : p.P) / BLOCK_K;
         if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, (uint32_t)bn);
             mbar_wait(&tmem_empty[as], aphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_EMPTY, as);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)as * BLOCK_N;
@@ -481,7 +591,7 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
     uint8_t* stg = smem + OFF_EPI + quarter * EPI_WARP_BYTES;
-    int q = 0, qphase = 0, as = 0, aphase = 0;
+    int q = 0, qphase = 0, as = 0, aphase = 0, ntiles = 0;
     for (;;) {
         mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, 100 + q);
         const TileInfo ti = ring[q];
@@ -489,7 +599,7 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         if (ti.kind < 0) break;
         const int N = ti.kind == 0 ? p.P : p.H;
-        const int n0 = ti.ntile * BLOCK_N;
+        const int n0 = ti.ntile * ti.bn;
         const __nv_bfloat16* bias = ti.kind == 0 ? (p.b_up ? p.b_up + (size_t)ti.le * p.P : nullptr)
                                                  : (p.b_down ? p.b_down + (size_t)ti.le * p.H : nullptr);
         // destination rows: GEMM0 -> local h staging; GEMM1 -> the SOURCE rank's return buffer (peer store),
@@ -501,7 +611,7 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             const int e_global = p.rank * p.nLx + ti.le;
             out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)ti.mblk * BLOCK_M) * p.H;
         }
-        const int nchunks = min(BLOCK_N / 64, (N - n0) / 64);
+        const int nchunks = min(ti.bn / 64, (N - n0) / 64);
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
@@ -561,6 +671,8 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         if (ti.kind == 0) fence_proxy_async_global();   // h will be read by TMA (async proxy) on other SMs
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid == EPI_WARP0 * 32) {
+            if (ntiles < 48) trace_stamp(p, 64 + ntiles);
+            ++ntiles;
             if (ti.kind == 0) {
                 fence_proxy_async_global();
                 red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + ti.mblk, 1u);
@@ -614,33 +726,48 @@ __device__ __forceinline__ void combine_phase(const FmParams& p, int t0, int n_t
             }
         }
         __nv_bfloat16* orow = p.out + (size_t)t * H;
-        for (int h = lane * 8; h < H; h += 256) {
-            float acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-            if (k == 1) {
-                uint4 v = make_uint4(0, 0, 0, 0);
+        if (k == 1) {
+            for (int h = lane * 8; h < H; h += 256) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
                 if (keep[0]) v = ld_global_v4(yrow[0] + h);
                 st_global_v4(orow + h, v);
-                continue;
             }
+            continue;
+        }
+        for (int hg = 0; hg < H; hg += 512) {
+            uint4 yv[8][2];   // all loads of this column group are issued before the arithmetic
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (j < k && keep[j]) {
-                    float y[8];
-                    unpack8(ld_global_v4(yrow[j] + h), y);
+            for (int j = 0; j < 8; ++j)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float qv = rne_bf16(__fdividef(y[i], mcw));
-                        const float term = rne_bf16(pw[j] * qv);
-                        acc[i] = rne_bf16(acc[i] + term);
+                for (int i = 0; i < 2; ++i) {
+                    const int h = hg + i * 256 + lane * 8;
+                    if (j < k && keep[j] && h < H) yv[j][i] = ld_global_v4(yrow[j] + h);
+                }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int h = hg + i * 256 + lane * 8;
+                if (h >= H) continue;
+                float acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j < k && keep[j]) {
+                        float y[8];
+                        unpack8(yv[j][i], y);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float qv = rne_bf16(__fdividef(y[q], mcw));
+                            const float term = rne_bf16(pw[j] * qv);
+                            acc[q] = rne_bf16(acc[q] + term);
+                        }
                     }
                 }
+                uint4 o;
+                o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+                o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+                st_global_v4(orow + h, o);
             }
-            uint4 o;
-            o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-            o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-            st_global_v4(orow + h, o);
         }
     }
 }
@@ -667,9 +794,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
                 *p.disp_done = 0u;
             }
         }
+        if (tid == 0) trace_stamp(p, 0);
         gate_phase(p, smem, t0, n_tok);
+        if (tid == 0) trace_stamp(p, 1);
         grid_barrier(p);
+        if (tid == 0) trace_stamp(p, 2);
         dispatch_phase(p, smem, t0, n_tok);
+        if (tid == 0) trace_stamp(p, 3);
     } else if (blockIdx.x == 0 && tid == 0) {
         *p.claim = 0u;   // debug re-run of later phases on the previous routing
     }
@@ -685,7 +816,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
             uint64_t* sched_empty = sched_full + NSCHED;
             for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
-            for (int i = 0; i < NSCHED; ++i) { mbar_init(&sched_full[i], 1); mbar_init(&sched_empty[i], 129); }
+            uint64_t* prod_take = sched_empty + NSCHED;
+            for (int i = 0; i < NSCHED; ++i) {
+                mbar_init(&sched_full[i], 1);
+                mbar_init(&sched_empty[i], 130);  // producer + MMA lane + 128 epilogue threads
+                mbar_init(&prod_take[i], 1);
+            }
             fence_mbar_init();
         }
         if (warp == 0 && (tid & 31) == 0) {
@@ -698,8 +834,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
         tcgen05_fence_after();
         const uint32_t tmem_base = *tmem_ptr;
 
+        if (tid == 0) trace_stamp(p, 4);
         if (warp == 0) ffn_producer(p, smem, bars);
         else if (warp == 1) ffn_mma(p, smem, bars, tmem_base);
+        else if (warp == 3) ffn_scheduler(p, smem, bars);
         else if (warp >= EPI_WARP0) ffn_epilogue(p, smem, bars, tmem_base);
 
         tcgen05_fence_before();
@@ -708,8 +846,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
             tcgen05_fence_after();
             tmem_dealloc(tmem_base, TMEM_COLS);
         }
+        if (tid == 0) trace_stamp(p, 5);
     }
-    if (p.phase_mask & 4u) combine_phase(p, t0, n_tok);
+    if (p.phase_mask & 4u) {
+        combine_phase(p, t0, n_tok);
+        __syncthreads();
+        if (tid == 0) trace_stamp(p, 6);
+    }
 }
 
 }  // namespace fm

@@ -28,6 +28,7 @@ _BUFFER_SPECS = {
     "ret_y": (_lib.BUF_RET_Y, np.uint16),
     "gate_out": (_lib.BUF_GATE_OUT, np.uint16),
     "recv_cnt": (_lib.BUF_RECV_CNT, np.int32),
+    "trace": (_lib.BUF_TRACE, np.uint64),
 }
 
 
@@ -180,6 +181,9 @@ class MoEContext:
                                                expert_weights.data_ptr(), bu, bd, out_host.data_ptr(), stream))
         return out_host
 
+    def set_trace(self, enable: bool) -> None:
+        _lib.check(self._L.fm_set_trace(self._ctx, 1 if enable else 0))
+
     def check(self) -> None:
         """Raise if the last kernel reported a protocol timeout (call after a synchronise)."""
         _lib.check(self._L.fm_check(self._ctx))
@@ -202,7 +206,7 @@ class MoEContext:
         npk = d["world"] * d["num_local_experts"]
         shapes = {"topk_idx": (S, k), "topk_w": (S, k), "mcw": (S,), "slot": (S, k), "counts": (E,),
                   "recv_x": (npk, d["pEC"], H), "hidden": (npk, d["pEC"], P), "ret_y": (E, d["pEC"], H),
-                  "gate_out": (S, E), "recv_cnt": (npk,)}
+                  "gate_out": (S, E), "recv_cnt": (npk,), "trace": (d["num_sms"], 128)}
         return arr.reshape(shapes[name])
 
     @property

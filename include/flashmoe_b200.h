@@ -121,6 +121,8 @@ FM_API int fm_moe_forward_host(fm_ctx_t* ctx, const void* x_host, const void* ga
 FM_API int fm_check(fm_ctx_t* ctx);
 FM_API int fm_set_timeout_ms(fm_ctx_t* ctx, uint32_t ms);
 FM_API uint64_t fm_launch_count(const fm_ctx_t* ctx);
+/* Per-CTA phase / tile time stamps into FM_BUF_TRACE (profiling aid; off by default). */
+FM_API int fm_set_trace(fm_ctx_t* ctx, int enable);
 
 /* ---- inspection (tests / debugging): copy an internal device buffer to host memory after synchronising ---- */
 enum fm_buffer {
@@ -133,7 +135,8 @@ enum fm_buffer {
     FM_BUF_HIDDEN = 6,   /* bf16  [W, nLx, pEC, P]  h = act(x W_up^T + b) staging */
     FM_BUF_RET_Y = 7,    /* bf16  [E, pEC, H]       expert outputs returned to this rank */
     FM_BUF_GATE_OUT = 8, /* bf16  [S, E]  full softmax row (reference gateOut[S,PX] without the padding columns) */
-    FM_BUF_RECV_CNT = 9  /* int32 [W, nLx] rows received per (source rank, local expert) in the last forward */
+    FM_BUF_RECV_CNT = 9, /* int32 [W, nLx] rows received per (source rank, local expert) in the last forward */
+    FM_BUF_TRACE = 10    /* u64   [num_sms, 128] %globaltimer stamps of the last forward (fm_set_trace) */
 };
 FM_API int fm_buffer_bytes(const fm_ctx_t* ctx, int which, size_t* bytes);
 FM_API int fm_read_buffer(fm_ctx_t* ctx, int which, void* host_dst, size_t bytes);

@@ -108,6 +108,32 @@ def stage(args):
             for _ in range(n): ctx.forward(xd, wgd, wed, out=out, phase_mask=mask)
             ev1.record(); ctx.synchronize()
             print(f"  phase {nm}: {ev0.elapsed_time(ev1)/n*1e3:.1f} us")
+    if st == "trace":
+        out = ctx.forward(xd, wgd, wed); ctx.synchronize()
+        for _ in range(3): ctx.forward(xd, wgd, wed, out=out)
+        ctx.set_trace(True)
+        ctx.forward(xd, wgd, wed, out=out); ctx.synchronize()
+        tr = ctx.read("trace").astype(np.int64)
+        t00 = tr[:, 0].min()
+        names = ["start", "gate", "barrier", "dispatch", "ffn_start", "ffn_end", "combine_end"]
+        for i, nm in enumerate(names):
+            v = (tr[:, i] - t00) / 1e3
+            print(f"  {nm:12s} min {v.min():8.1f} med {np.median(v):8.1f} max {v.max():8.1f} us")
+        ready = tr[:, 16:64]; done = tr[:, 64:112]
+        ntiles = (ready > 0).sum(1)
+        print(f"  tiles per CTA min {ntiles.min()} med {np.median(ntiles)} max {ntiles.max()} total {ntiles.sum()}")
+        durs = []; gaps = []
+        for c in range(tr.shape[0]):
+            n = ntiles[c]
+            for i in range(n):
+                prev_done = done[c, i - 1] if i > 0 else tr[c, 4]
+                durs.append((done[c, i] - max(prev_done, ready[c, i])) / 1e3)
+        durs = np.array(durs)
+        print(f"  tile service time (us): min {durs.min():.1f} p10 {np.percentile(durs,10):.1f} med {np.median(durs):.1f} p90 {np.percentile(durs,90):.1f} max {durs.max():.1f}")
+        last_done = np.array([done[c, ntiles[c]-1] if ntiles[c] else tr[c,4] for c in range(tr.shape[0])])
+        v = (last_done - t00) / 1e3
+        print(f"  last tile stored: min {v.min():.1f} med {np.median(v):.1f} max {v.max():.1f} us")
+        np.save("gpurun_out/trace_%s.npy" % args.cfg, tr)
     ctx.close()
 
 
@@ -117,7 +143,7 @@ if __name__ == "__main__":
     ap.add_argument("--noscale", action="store_true"); ap.add_argument("--all-experts", dest="all_experts", action="store_true")
     args = ap.parse_args()
     if args.stage == "all":
-        for st in ("gate", "ffn", "combine", "full", "time"):
+        for st in ("gate", "ffn", "combine", "full", "time", "trace"):
             print(f"===== stage {st} ({args.cfg}) =====", flush=True)
             cmd = [sys.executable, __file__, "--cfg", args.cfg, "--stage", st] + (["--noscale"] if args.noscale else [])
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
