@@ -390,11 +390,14 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         blocks.push_back(b);
         start += d.TCM * (kind == 0 ? ctx->TN0 : ctx->TN1);
     };
+    // GEMM1 of a packet is queued `lag` packets after its GEMM0 so the h row blocks it needs are complete when claimed
+    int lag = env_int("FM_G1_LAG", 2);
+    if (lag < 1) lag = 1;
     for (size_t i = 0; i < order.size(); ++i) {
         push(0, order[i]);
-        if (i >= 1) push(1, order[i - 1]);
+        if ((int)i >= lag) push(1, order[i - lag]);
     }
-    push(1, order.back());
+    for (size_t i = order.size() > (size_t)lag ? order.size() - lag : 0; i < order.size(); ++i) push(1, order[i]);
     ctx->num_blocks = (int)blocks.size();
     ctx->total_items = start;
     fm::TileBlock sentinel;

@@ -252,6 +252,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             }
         }
         __syncthreads();
+        if (tid == 0) trace_stamp(p, 11);
         // thread-per-token softmax + top-k, the same per-thread recurrence the reference runs after its transpose
         for (int ti = tid; ti < n_sub; ti += NUM_THREADS) {
             float* l = logit_s + ti * ldl;
@@ -295,6 +296,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }
         __syncthreads();
     }
+    if (tid == 0) trace_stamp(p, 12);
     // position of every (token, pick) among this chunk's selections of the same expert, ascending token order
     for (int e = tid; e < E; e += NUM_THREADS) {
         int cnt = 0;
@@ -334,6 +336,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         if (cur_e >= 0 && part != 0) atomicAdd(&base_s[cur_e], part);
     }
     __syncthreads();
+    if (tid == 0) trace_stamp(p, 8);
     for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
         const int t = t0 + ti;
         __nv_bfloat16* dst[8];
@@ -371,6 +374,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         }
     }
     __syncthreads();
+    if (tid == 0) trace_stamp(p, 9);
     if (tid == 0) {
         fence_acq_rel_sys();  // this CTA's row stores (observed through the barrier) before the counter bump
         const unsigned int old = atom_acq_rel_gpu_add_u32(p.disp_done, 1u);
@@ -512,7 +516,7 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
             const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
             const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
             const uint32_t tx = (uint32_t)(A_STAGE_BYTES + ti.bn * BLOCK_K * 2);
-            const int take_at = max(0, ti.nk - p.claim_ahead_kb);
+            const int take_at = min(ti.nk - 1, max(0, ti.nk - p.claim_ahead_kb));
             for (int kb = 0; kb < ti.nk; ++kb) {
                 if (kb == take_at) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
@@ -697,61 +701,47 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
 // Deterministic gather (no atomics, no zero-fill pass); for k == 2 it equals the reference's atomicAdd result
 // exactly because bf16 addition commutes and 0 + a is exact.
 // ============================================================================================================
-__device__ __forceinline__ void combine_phase(const FmParams& p, int t0, int n_tok) {
+template <int KMAX, int PIECES>
+__device__ __forceinline__ void combine_rows(const FmParams& p, int t0, int n_tok, const int* c_e, const int* c_s,
+                                             const float* c_w, const float* c_m) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int H = p.H, k = p.k;
     for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
-        const int t = t0 + ti;
-        const __nv_bfloat16* yrow[8];
-        float pw[8];
-        bool keep[8];
-        const float mcw = p.mcw[t];
+        const __nv_bfloat16* yrow[KMAX];
+        float pw[KMAX];
+        bool keep[KMAX];
+        const float mcw = c_m[ti];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < KMAX; ++j) {
             keep[j] = false;
             yrow[j] = nullptr;
             pw[j] = 0.0f;
             if (j < k) {
-                const int e = p.topk_idx[(size_t)t * k + j];
-                const int s = p.slot[(size_t)t * k + j];
-                pw[j] = __bfloat162float(p.topk_w[(size_t)t * k + j]);
+                const int s = c_s[ti * k + j];
+                pw[j] = c_w[ti * k + j];
                 keep[j] = s < p.EC;
-                if (keep[j]) {
-                    const unsigned long long* fl = p.ret_flag + (size_t)e * p.TCM + (s / BLOCK_M);
-                    SpinGuard g;
-                    while ((ld_acquire_sys_u64(fl) >> 32) != p.epoch)
-                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_RET_FLAG, e, s, t);
-                    yrow[j] = p.ret_y + ((size_t)e * p.pEC + s) * H;
-                }
+                yrow[j] = p.ret_y + ((size_t)c_e[ti * k + j] * p.pEC + (keep[j] ? s : 0)) * H;
             }
         }
-        __nv_bfloat16* orow = p.out + (size_t)t * H;
-        if (k == 1) {
-            for (int h = lane * 8; h < H; h += 256) {
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (keep[0]) v = ld_global_v4(yrow[0] + h);
-                st_global_v4(orow + h, v);
-            }
-            continue;
-        }
-        for (int hg = 0; hg < H; hg += 512) {
-            uint4 yv[8][2];   // all loads of this column group are issued before the arithmetic
+        __nv_bfloat16* orow = p.out + (size_t)(t0 + ti) * H;
+        for (int hg = 0; hg < H; hg += PIECES * 256) {
+            uint4 yv[KMAX][PIECES];   // every load of this column group is issued before the arithmetic
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < KMAX; ++j)
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < PIECES; ++i) {
                     const int h = hg + i * 256 + lane * 8;
                     if (j < k && keep[j] && h < H) yv[j][i] = ld_global_v4(yrow[j] + h);
                 }
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < PIECES; ++i) {
                 const int h = hg + i * 256 + lane * 8;
                 if (h >= H) continue;
                 float acc[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc[q] = 0.0f;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < KMAX; ++j) {
                     if (j < k && keep[j]) {
                         float y[8];
                         unpack8(yv[j][i], y);
@@ -769,6 +759,50 @@ __device__ __forceinline__ void combine_phase(const FmParams& p, int t0, int n_t
                 st_global_v4(orow + h, o);
             }
         }
+    }
+}
+
+__device__ __forceinline__ void combine_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = p.H, k = p.k;
+    // the pipeline stage area is free again: stage this chunk's routing records, and let one thread per (token, pick)
+    // poll its return flag so the waits overlap instead of chaining per token
+    int* c_e = reinterpret_cast<int*>(smem);
+    int* c_s = c_e + G_SEL_MAX;
+    float* c_w = reinterpret_cast<float*>(c_s + G_SEL_MAX);
+    float* c_m = c_w + G_SEL_MAX;
+    const int n = n_tok * k;
+    for (int i = tid; i < n; i += NUM_THREADS) {
+        const size_t gi = (size_t)t0 * k + i;
+        const int e = p.topk_idx[gi];
+        const int s = p.slot[gi];
+        c_e[i] = e;
+        c_s[i] = s;
+        c_w[i] = __bfloat162float(p.topk_w[gi]);
+        if (s < p.EC) {
+            const unsigned long long* fl = p.ret_flag + (size_t)e * p.TCM + (s / BLOCK_M);
+            SpinGuard g;
+            while ((ld_acquire_sys_u64(fl) >> 32) != p.epoch)
+                g.tick(p.dbg, p.timeout_ns, FM_TRAP_RET_FLAG, e, s, t0 + i / k);
+        }
+    }
+    for (int i = tid; i < n_tok; i += NUM_THREADS) c_m[i] = p.mcw[t0 + i];
+    __syncthreads();
+    if (k == 1) {
+        for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
+            const bool keep = c_s[ti] < p.EC;
+            const __nv_bfloat16* yrow = p.ret_y + ((size_t)c_e[ti] * p.pEC + (keep ? c_s[ti] : 0)) * H;
+            __nv_bfloat16* orow = p.out + (size_t)(t0 + ti) * H;
+            for (int h = lane * 8; h < H; h += 256) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (keep) v = ld_global_v4(yrow + h);
+                st_global_v4(orow + h, v);
+            }
+        }
+    } else if (k == 2) {
+        combine_rows<2, 4>(p, t0, n_tok, c_e, c_s, c_w, c_m);
+    } else {
+        combine_rows<8, 1>(p, t0, n_tok, c_e, c_s, c_w, c_m);
     }
 }
 
@@ -849,7 +883,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
         if (tid == 0) trace_stamp(p, 5);
     }
     if (p.phase_mask & 4u) {
-        combine_phase(p, t0, n_tok);
+        combine_phase(p, smem, t0, n_tok);
         __syncthreads();
         if (tid == 0) trace_stamp(p, 6);
     }

@@ -115,8 +115,9 @@ def stage(args):
         ctx.forward(xd, wgd, wed, out=out); ctx.synchronize()
         tr = ctx.read("trace").astype(np.int64)
         t00 = tr[:, 0].min()
-        names = ["start", "gate", "barrier", "dispatch", "ffn_start", "ffn_end", "combine_end"]
+        names = ["start", "gate", "barrier", "dispatch", "ffn_start", "ffn_end", "combine_end", "", "disp_base", "disp_rows", "", "gate_gemv", "gate_softmax"]
         for i, nm in enumerate(names):
+            if not nm: continue
             v = (tr[:, i] - t00) / 1e3
             print(f"  {nm:12s} min {v.min():8.1f} med {np.median(v):8.1f} max {v.max():8.1f} us")
         ready = tr[:, 16:64]; done = tr[:, 64:112]
