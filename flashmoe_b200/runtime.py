@@ -47,6 +47,20 @@ def env_rank_world() -> Tuple[int, int, int]:
     return rank, world, local
 
 
+def exchange_blobs(mine: bytes, world: int, group=None) -> bytes:
+    """All-gather one fixed-size byte string per rank over torch.distributed (any backend) and return them
+    concatenated in rank order -- the out-of-band channel for the CUDA IPC handles of the symmetric slabs."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("world > 1 needs an initialised torch.distributed process group")
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    if any(len(g) != len(mine) for g in gathered):
+        raise RuntimeError("peers exported handles of different sizes")
+    return b"".join(gathered)
+
+
 def _check_tensor(name: str, t: torch.Tensor, device: torch.device) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be CUDA tensor")
@@ -87,13 +101,9 @@ class MoEContext:
         (replaces nvshmem_malloc + nvshmem_ptr, reference bootstrap.cuh:359-360,442-443)."""
         import torch.distributed as dist
 
-        if not dist.is_initialized():
-            raise RuntimeError("world > 1 needs an initialised torch.distributed process group")
         handle = (ctypes.c_ubyte * _lib.FM_IPC_HANDLE_BYTES)()
         _lib.check(self._L.fm_symm_export(self._ctx, handle))
-        gathered = [None] * self.world
-        dist.all_gather_object(gathered, bytes(handle), group=group)
-        blob = b"".join(gathered)
+        blob = exchange_blobs(bytes(handle), self.world, group)
         assert len(blob) == self.world * _lib.FM_IPC_HANDLE_BYTES
         _lib.check(self._L.fm_symm_attach_ipc(self._ctx, blob))
         torch.cuda.synchronize(self.device)

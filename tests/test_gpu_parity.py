@@ -1,0 +1,230 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (MoEContext -> ctypes -> libflashmoe_b200.so), against
+the CPU oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full
+single-GPU size -- through size-independent properties.  Needs a B200 (pytest -m gpu)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from flashmoe_b200.config import BASELINE_CONFIGS, MoEConfig
+from oracle import moe_oracle as mo
+from tests.test_oracle import load_golden
+from tests.util import check_output, check_topk, make_inputs, run_oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _ctx(cfg, **kw):
+    from flashmoe_b200.runtime import MoEContext
+
+    return MoEContext(cfg, timeout_ms=5000, **kw)
+
+
+def _run(cfg, x, wg, we, bu=None, bd=None):
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    args = [t.to(dev) for t in (x, wg, we)]
+    out = ctx.forward(*args, bias_up=None if bu is None else bu.to(dev), bias_down=None if bd is None else bd.to(dev))
+    ctx.synchronize()
+    got = {"out": mo.to_bits(out.cpu().reshape(cfg.S, cfg.H)), "topk_idx": ctx.read("topk_idx"), "slot": ctx.read("slot"),
+           "counts": ctx.read("counts"), "mcw": ctx.read("mcw"), "gate_out": ctx.read("gate_out"),
+           "topk_w": ctx.read("topk_w")}
+    ctx.close()
+    return got
+
+
+def _compare(cfg, got, ref):
+    mism = check_topk(got["topk_idx"], ref)
+    if not mism.any():  # identical routing => integer bookkeeping must be exact
+        assert (got["slot"] == ref.slot).all()
+        assert (got["counts"] == ref.counts).all()
+    np.testing.assert_allclose(got["mcw"][~mism], ref.mcw[~mism], rtol=2e-6)
+    assert (got["gate_out"] == ref.gate_out).mean() > 0.995  # bf16 probabilities; rare 1-ulp flips from ex2.approx
+    return check_output(got["out"], ref.out, rows_ok=~mism)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_matches_committed_golden_vectors(path):
+    cfg, z = load_golden(path)
+    x, wg, we, bu, bd = make_inputs(cfg, seed=int(z["seed"]), scaled=bool(z["scaled"]), bias=bool(z["bias"]))
+    got = _run(cfg, x, wg, we, bu, bd)
+    amb = z["ambiguous"]
+    mism = (got["topk_idx"] != z["topk_idx"]).any(axis=1)
+    assert not (mism & ~amb).any()
+    if not mism.any():
+        assert (got["slot"] == z["slot"]).all() and (got["counts"] == z["counts"]).all()
+    check_output(got["out"], z["out"], rows_ok=~mism, what="out vs golden")
+
+
+CASES = {
+    "tiny": MoEConfig(num_experts=4, expert_top_k=2, sequence_len=128, hidden_size=64, intermediate_size=256),
+    "small_drop": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=512, hidden_size=256, intermediate_size=512),
+    "small_nodrop": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=512, hidden_size=256, intermediate_size=512,
+                              drop_tokens=0),
+    "configA_top1": BASELINE_CONFIGS["A"],
+    "gelu_cf2": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=256, hidden_size=128, intermediate_size=384,
+                          hidden_act=1, capacity_factor=2),
+    "ragged_dims": MoEConfig(num_experts=6, expert_top_k=3, sequence_len=384, hidden_size=320, intermediate_size=448),
+    "E32_k2": MoEConfig(num_experts=32, expert_top_k=2, sequence_len=1024, hidden_size=512, intermediate_size=512),
+    "E64_k4": MoEConfig(num_experts=64, expert_top_k=4, sequence_len=512, hidden_size=256, intermediate_size=256),
+    "E128_k2": MoEConfig(num_experts=128, expert_top_k=2, sequence_len=1024, hidden_size=256, intermediate_size=256),
+    "E1_dense": MoEConfig(num_experts=1, expert_top_k=1, sequence_len=256, hidden_size=128, intermediate_size=512),
+    "k8": MoEConfig(num_experts=16, expert_top_k=8, sequence_len=256, hidden_size=128, intermediate_size=256),
+    "multi_seq": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=256, mini_batch=3, hidden_size=128,
+                           intermediate_size=256),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_parity_with_oracle(name):
+    cfg = CASES[name]
+    x, wg, we, _, _ = make_inputs(cfg, seed=100 + len(name))
+    _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
+
+
+def test_parity_with_bias_and_gelu():
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=256, hidden_size=256, intermediate_size=512, hidden_act=1)
+    x, wg, we, bu, bd = make_inputs(cfg, seed=7, bias=True)
+    _compare(cfg, _run(cfg, x, wg, we, bu, bd), run_oracle(cfg, x, wg, we, bu, bd))
+
+
+def test_unscaled_weights_like_the_reference_harness():
+    # torch.randn weights without scaling (reference worker.py:56-58): near-one-hot softmax, |y| ~ 1e3
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=512, hidden_size=256, intermediate_size=512)
+    x, wg, we, _, _ = make_inputs(cfg, seed=8, scaled=False)
+    _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
+
+
+def test_exp_underflow_corner_matches_reference_semantics():
+    # Appendix A.4 on the GPU: all but one probability flush to zero; picks continue in index order
+    cfg = MoEConfig(num_experts=4, expert_top_k=3, sequence_len=128, hidden_size=64, intermediate_size=64)
+    x = torch.zeros(1, 128, 64)
+    x[..., 0] = 1.0
+    wg_eff = torch.zeros(4, 64)
+    wg_eff[:, 0] = torch.tensor([100.0, -200.0, -150.0, -120.0])
+    wg = wg_eff.reshape(-1).view(64, 4)  # the [H,E] tensor whose flat view is wg_eff
+    g = torch.Generator().manual_seed(9)
+    we = torch.randn(4, 2, 64, 64, generator=g) * 0.1
+    got = _run(cfg, x.bfloat16(), wg.bfloat16(), we.bfloat16())
+    assert (got["topk_idx"] == np.array([0, 1, 2])).all()
+    _compare(cfg, got, run_oracle(cfg, x.bfloat16(), wg.bfloat16(), we.bfloat16()))
+
+
+def test_all_tokens_to_one_expert_capacity_drop():
+    cfg = MoEConfig(num_experts=4, expert_top_k=1, sequence_len=256, hidden_size=64, intermediate_size=128)
+    x = torch.ones(1, 256, 64) * 0.5
+    wg_eff = torch.zeros(4, 64)
+    wg_eff[2] = 1.0
+    wg = wg_eff.reshape(-1).view(64, 4)
+    g = torch.Generator().manual_seed(10)
+    we = (torch.randn(4, 2, 128, 64, generator=g) * 0.2).bfloat16()
+    got = _run(cfg, x.bfloat16(), wg.bfloat16(), we)
+    assert got["counts"].tolist() == [0, 0, 256, 0]
+    assert (got["slot"][:, 0] == np.arange(256)).all()
+    out = mo.bits_to_f32(got["out"])
+    assert (out[cfg.EC:] == 0).all() and (out[:cfg.EC] != 0).any()
+    _compare(cfg, got, run_oracle(cfg, x.bfloat16(), wg.bfloat16(), we))
+
+
+def test_full_size_config_B_parity_and_properties():
+    """BASELINE.json configs[1] (8 experts, top-2, seq 4096, d_model 1024, ffn 4096) at full size."""
+    cfg = BASELINE_CONFIGS["B"]
+    x, wg, we, _, _ = make_inputs(cfg, seed=1)
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    xd, wgd, wed = x.to(dev), wg.to(dev), we.to(dev)
+    out1 = ctx.forward(xd, wgd, wed).clone()
+    ctx.synchronize()
+    topk = ctx.read("topk_idx")
+    slot = ctx.read("slot")
+    counts = ctx.read("counts")
+    # property: idempotence / determinism across launches (epoch-tagged flags, no stale state)
+    for _ in range(3):
+        out2 = ctx.forward(xd, wgd, wed)
+    ctx.synchronize()
+    assert torch.equal(out1, out2)
+    # property: capacity accounting -- slots of each expert are a permutation of 0..count-1, kept = min(count, EC)
+    for e in range(cfg.E):
+        s = np.sort(slot[topk == e])
+        assert (s == np.arange(len(s))).all() and len(s) == counts[e]
+    assert counts.sum() == cfg.S * cfg.k
+    recv = ctx.read("recv_cnt")
+    assert (recv == np.minimum(counts, cfg.EC)).all()
+    # property: dispatch is an exact row copy (checksum of checksums over the received rows)
+    rx = ctx.read("recv_x").astype(np.uint64)
+    xb = mo.to_bits(x.reshape(cfg.S, cfg.H)).astype(np.uint64)
+    row_sum = xb.sum(axis=1)
+    kept = slot < cfg.EC
+    want = sum(int(row_sum[t]) for t, j in zip(*np.nonzero(kept)))
+    have = sum(int(rx[e, :recv[e]].sum()) for e in range(cfg.E))
+    assert want == have
+    # property: a token routed twice to dropped slots yields an all-zero row, never garbage
+    both_dropped = ~kept.any(axis=1)
+    o = mo.to_bits(out1.cpu().reshape(cfg.S, cfg.H))
+    assert (o[both_dropped] == 0).all()
+    # full-size oracle comparison (~1.5 s of CPU)
+    ref = run_oracle(cfg, x, wg, we)
+    mism = check_topk(topk, ref)
+    check_output(o, ref.out, rows_ok=~mism)
+    # permutation property: permuting tokens permutes routing decisions and (un-dropped) outputs
+    perm = torch.randperm(cfg.S, generator=torch.Generator().manual_seed(3))
+    xp = x.reshape(cfg.S, cfg.H)[perm].reshape(x.shape).contiguous()
+    ctx.forward(xp.to(dev), wgd, wed)
+    ctx.synchronize()
+    assert (ctx.read("topk_idx") == topk[perm.numpy()]).all()
+    ctx.close()
+
+
+def test_host_buffer_entry_point_equals_device_path():
+    cfg = CASES["small_drop"]
+    x, wg, we, _, _ = make_inputs(cfg, seed=21)
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    out_dev = ctx.forward(x.to(dev), wg.to(dev), we.to(dev))
+    ctx.synchronize()
+    out_host = ctx.forward_host(x.pin_memory(), wg.to(dev), we.to(dev))
+    assert torch.equal(out_host, out_dev.cpu())
+    ctx.close()
+
+
+def test_reference_style_argument_checks_raise_runtime_error():
+    cfg = CASES["tiny"]
+    x, wg, we, _, _ = make_inputs(cfg, seed=22)
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ctx.forward(x, wg.to(dev), we.to(dev))
+    with pytest.raises(RuntimeError, match="compiled S"):
+        ctx.forward(x[:, :64].contiguous().to(dev), wg.to(dev), we.to(dev))
+    with pytest.raises(RuntimeError, match="Gate weights"):
+        ctx.forward(x.to(dev), wg.t().contiguous().to(dev), we.to(dev))
+    with pytest.raises(RuntimeError, match="Expert count"):
+        ctx.forward(x.to(dev), wg.to(dev), we[:2].contiguous().to(dev))
+    with pytest.raises(RuntimeError, match="bfloat16"):
+        ctx.forward(x.float().to(dev), wg.to(dev), we.to(dev))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        ctx.forward(x.to(dev).transpose(0, 1).expand(128, 1, 64).transpose(0, 1)[:, :, ::1].as_strided((1, 128, 64), (1, 64, 1)),
+                    wg.to(dev), we.to(dev)) if False else ctx.forward(x.to(dev), wg.to(dev), we.to(dev).transpose(2, 3))
+    ctx.close()
+
+
+def test_module_level_C_api_single_process():
+    """flashmoe._C.initialize / moe_forward / finalize on the compiled configuration (config B)."""
+    import flashmoe
+    from flashmoe import _C
+
+    _C.initialize()
+    try:
+        cc = flashmoe.get_compiled_config()
+        assert cc["S"] == 4096 and cc["Element_size"] == 2 and _C.get_bookkeeping() == {"nLx": 8}
+        cfg = BASELINE_CONFIGS["B"]
+        x, wg, we, _, _ = make_inputs(cfg, seed=23)
+        out = _C.moe_forward(x.cuda(), wg.cuda(), we.cuda())
+        assert out.shape == x.shape and out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()
+        with pytest.raises(RuntimeError):
+            _C.initialize()
+    finally:
+        _C.finalize()
