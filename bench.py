@@ -117,12 +117,25 @@ class ClockSampler:
                 "reasons": sorted(n for n, b in names.items() if bits & b), "samples": len(inside)}
 
 
+def usable_cpus() -> int:
+    """Host threads this process may really use: CPU affinity capped by the cgroup CPU quota (the GPU box shows 128
+    CPUs but grants a quota of ~24; running MKL with 128 threads there is 5x slower than with 24-32)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, -(-int(quota) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_forward_tokens_per_s(cfg, budget_s, steps_hint=3):
     """Plain torch CPU MoE forward (oracle/torch_moe.py) of the bench workload on the host cores.  Returns
     (tokens/s, threads, description, seconds per step, tokens per step)."""
     from oracle import torch_moe
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(usable_cpus())
     x, wg, we = make_inputs(cfg, cfg.E, 0)
     S = cfg.S
     xs = x.reshape(S, cfg.H)
@@ -296,7 +309,7 @@ def main():
         dt = (time.perf_counter() - t0) / iters
         line["cpu_baseline"] = {"value": tokens / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{iters} forwards of {tokens} of {S} tokens (plain torch CPU MoE forward, "
-                                          f"oracle/torch_moe.py; {os.cpu_count()} host CPUs visible)"}
+                                          f"oracle/torch_moe.py; {os.cpu_count()} host CPUs visible, {usable_cpus()} usable under the cgroup quota)"}
     ctx.close()
     if world > 1:
         dist.barrier()
