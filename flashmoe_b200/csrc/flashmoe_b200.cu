@@ -103,6 +103,7 @@ struct fm_ctx {
     int tpc = 0;
     int TN0 = 0, TN1 = 0, num_pkts = 0, num_blocks = 0, total_items = 0;
     int bn0 = 256, bn1 = 256, claim_ahead_kb = 8;
+    bool pair = false;   // cta_group::2: two CTAs (one cluster) per 256-row tile
     uint32_t epoch = 0;
     unsigned long long bar_count = 0;
     unsigned long long timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
@@ -242,8 +243,10 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
         // (python_bindings.cu:104-119).  One tensor map per GEMM over the whole tensor with a per-expert row stride
         // of 2*P (resp. 2*H) rows is not expressible in 2-D, so rows are addressed as [nLx*2*P, H] / [nLx*2*H, P]:
         // expert i's W_up starts at row i*2*P, its W_down at row (i*2+1)*H of the [.,P] view.
-        if ((rc = make_tmap(&c->tm_b0, expert_w, (uint64_t)nLx * 2 * d.P, d.H, (uint32_t)c->bn0))) return rc;
-        if ((rc = make_tmap(&c->tm_b1, expert_w, (uint64_t)nLx * 2 * d.H, d.P, (uint32_t)c->bn1))) return rc;
+        // in pair mode each CTA of the pair stages half of the B tile's rows
+        const uint32_t bdiv = c->pair ? 2u : 1u;
+        if ((rc = make_tmap(&c->tm_b0, expert_w, (uint64_t)nLx * 2 * d.P, d.H, (uint32_t)c->bn0 / bdiv))) return rc;
+        if ((rc = make_tmap(&c->tm_b1, expert_w, (uint64_t)nLx * 2 * d.H, d.P, (uint32_t)c->bn1 / bdiv))) return rc;
         c->cached_expert_w = expert_w;
     }
     fm::FmParams p;
@@ -282,9 +285,28 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.dbg = c->dbg_dev;
     p.trace = c->trace_on ? c->trace : nullptr;
 
-    void* args[] = {&p};
-    FM_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel), dim3(c->grid),
-                                        dim3(fm::NUM_THREADS), args, (size_t)fm::SMEM_BYTES, stream));
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(c->grid);
+    lc.blockDim = dim3(fm::NUM_THREADS);
+    lc.dynamicSmemBytes = (size_t)fm::SMEM_BYTES;
+    lc.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: in-kernel spin waits + grid barrier
+    attrs[na].val.cooperative = 1;
+    ++na;
+    if (c->pair) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = 2;
+        attrs[na].val.clusterDim.y = 1;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    lc.attrs = attrs;
+    lc.numAttrs = na;
+    if (c->pair) FM_CUDA(cudaLaunchKernelEx(&lc, fm::fm_moe_forward_kernel<true>, p));
+    else FM_CUDA(cudaLaunchKernelEx(&lc, fm::fm_moe_forward_kernel<false>, p));
     c->launches += 1;
     return FM_OK;
 }
@@ -345,10 +367,12 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     d.num_sms = prop.multiProcessorCount;
     d.smem_bytes = fm::SMEM_BYTES;
 
-    FM_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel),
+    FM_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel<false>),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, fm::SMEM_BYTES));
+    FM_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel<true>),
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fm::SMEM_BYTES));
     int occ = 0;
-    FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fm::fm_moe_forward_kernel, fm::NUM_THREADS,
+    FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fm::fm_moe_forward_kernel<false>, fm::NUM_THREADS,
                                                           (size_t)fm::SMEM_BYTES));
     if (occ < 1) return fail(FM_ECUDA, "kernel does not fit on an SM (smem %d B)", fm::SMEM_BYTES);
 
@@ -357,6 +381,11 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->d = d;
     ctx->device = device;
     ctx->grid = d.num_sms;  // one persistent CTA per SM; all co-resident (spin waits + grid barrier)
+    {
+        const char* v = getenv("FM_PAIR");
+        ctx->pair = (v != nullptr && *v) ? atoi(v) != 0 : false;
+        if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
+    }
     ctx->tpc = ceil_div(d.S, ctx->grid);
     if ((long long)ctx->tpc * d.k > fm::G_SEL_MAX) {
         delete ctx;
@@ -388,7 +417,8 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         fm::TileBlock b;
         b.kind = kind; b.pkt = pkt; b.start = start; b.pad = 0;
         blocks.push_back(b);
-        start += d.TCM * (kind == 0 ? ctx->TN0 : ctx->TN1);
+        const int row_items = ctx->pair ? (d.TCM + 1) / 2 : d.TCM;  // a pair covers two 128-row blocks per item
+        start += row_items * (kind == 0 ? ctx->TN0 : ctx->TN1);
     };
     // GEMM1 of a packet is queued `lag` packets after its GEMM0 so the h row blocks it needs are complete when claimed
     // (default: all GEMM0 blocks first -- measured best on config B: 163 us vs 168 us with a lag of 2)

@@ -13,7 +13,7 @@
 //   phase C  combine   per token: gather the k returned rows, scale, bf16-accumulate (reference processor.cuh:27-205)
 //
 // CTA = 256 threads, one CTA per SM, all co-resident (cooperative launch).  In phase F the warps specialise:
-// warp 0 = tile claimer + TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+// warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warp 3 = tile claimer, warps 4-7 = epilogue
 // (TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced 16-byte global / peer stores).
 #pragma once
 #include <cuda.h>
@@ -30,7 +30,6 @@ constexpr int BLOCK_M = 128;   // token rows per tile (= reference BLOCK_M)
 constexpr int BLOCK_N = 256;   // max output columns per tile (one tcgen05.mma N); per-GEMM width is p.bn[kind]
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int NSCHED = 4;
 constexpr int NUM_THREADS = 256;
 constexpr int NUM_WARPS = NUM_THREADS / 32;
@@ -39,18 +38,30 @@ constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators
 constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [7] tiles, [16+i] tile i ready, [64+i] tile i stored
 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                  // 16 KiB
-constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;                  // 32 KiB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;            // 48 KiB
+constexpr int PIPE_BYTES = 196608;                                    // 4 x 48 KiB (solo) = 6 x 32 KiB (CTA pair)
+constexpr int MAX_STAGES = 6;
 constexpr int EPI_ROW_BYTES = 144;                                    // 128 B of payload + 16 B pad (bank spread)
 constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
-constexpr int OFF_EPI = STAGES * STAGE_BYTES;                         // 196608
+constexpr int OFF_EPI = PIPE_BYTES;                                   // 196608
 constexpr int OFF_BARS = OFF_EPI + 4 * EPI_WARP_BYTES;                // 215040
-constexpr int NUM_BARS = 2 * STAGES + 4 + 3 * NSCHED;                 // 24
-constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 215232
-constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 48;
+// barriers: full[6] empty[6] tmem_full[2] tmem_empty[2] sched_full[4] sched_empty[4] prod_take[4]
+constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_TMEM_FULL = 2 * MAX_STAGES, BAR_TMEM_EMPTY = BAR_TMEM_FULL + 2;
+constexpr int BAR_SCHED_FULL = BAR_TMEM_EMPTY + 2, BAR_SCHED_EMPTY = BAR_SCHED_FULL + NSCHED;
+constexpr int BAR_PROD_TAKE = BAR_SCHED_EMPTY + NSCHED;
+constexpr int NUM_BARS = BAR_PROD_TAKE + NSCHED;                      // 28
+constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 215264 (16-byte aligned)
+constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
 constexpr int SMEM_USED = OFF_MISC + 64;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                          // + slack for manual 1 KiB alignment
+static_assert(OFF_RING % 16 == 0, "ring entries are copied with 16-byte accesses");
+
+template <bool PAIR>
+struct PipeCfg {   // solo: one CTA per 128x256 tile; pair: two CTAs share one 256x256 tile (cta_group::2)
+    static constexpr int STAGES = PAIR ? 6 : 4;
+    static constexpr int B_ROWS_DIV = PAIR ? 2 : 1;                   // each CTA of a pair stages half of the B rows
+    static constexpr int STAGE_BYTES = PIPE_BYTES / STAGES;           // 32 KiB / 48 KiB
+};
 
 // gate-phase aliases of the (not yet used) pipeline stage area
 constexpr int G_OFF_WG = 0;              // bf16 [EG][Hc]           <= 64 KiB
@@ -407,30 +418,46 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
 //   j-1 (one packet of lag so the h row-block a GEMM1 tile needs is normally complete when it is claimed).
 //   item -> (row block m fastest, column tile n).  A GEMM1 tile waits for g0_done[pkt][m] == TN0.
 // ============================================================================================================
-struct TileInfo {     // 48 bytes, written by the scheduler warp, read by the producer, MMA and epilogue warps
+struct TileInfo {     // 64 bytes, written by the (leader's) scheduler warp, read by producer / MMA / epilogue warps
     int kind;         // 0 GEMM0, 1 GEMM1, -1 stop
     int pkt;          // local packet index src * nLx + le
-    int mblk;
+    int mblk;         // row block of cluster rank 0 (rank 1 of a pair works on mblk + 1)
     int ntile;
-    int rows;         // valid rows in this row block
+    int rows[2];      // valid rows of the row block of cluster rank 0 / 1
     int src;
     int le;
     int bn;           // tile width
     int nk;           // k-blocks
-    int a_row;        // TMA row coordinate of the A tile
-    int b_row;        // TMA row coordinate of the B tile
-    int pad;
+    int a_row;        // TMA row coordinate of rank 0's A tile (rank 1: + 128)
+    int b_row;        // TMA row coordinate of the B tile (rank 1 of a pair: + bn/2)
+    int pad[4];
 };
+static_assert(sizeof(TileInfo) == 64, "TileInfo must be 4 x 16 bytes");
 
-// warp 3: claims work items and resolves their dependencies AHEAD of the TMA producer, so the atomic, the packet flag
-// and the h-row-block counter round trips overlap the previous tile's loads (the job of the reference's OS CTA:
-// subscriber decode + scheduler doorbells, os/subscriber.cuh, os/scheduler.cuh -- here one warp per CTA, no queues).
+template <bool PAIR>
+__device__ __forceinline__ void wait_sched_full(const FmParams& p, uint64_t* bar, uint32_t parity, unsigned int info) {
+    if (PAIR) mbar_wait_cluster(bar, parity, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, info);  // data came over DSMEM
+    else mbar_wait(bar, parity, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, info);
+}
+// consumers of a ring slot release it on the LEADER's barrier (the scheduler lives there)
+template <bool PAIR>
+__device__ __forceinline__ void release_to_leader(uint64_t* bar, uint32_t crank) {
+    if (PAIR && crank != 0) mbar_arrive_cluster(bar, 0);
+    else mbar_arrive(bar);
+}
+
+// warp 3 (leader CTA in pair mode): claims work items and resolves their dependencies AHEAD of the TMA producer, so the
+// atomic, the packet-flag and the h-row-block-counter round trips overlap the previous tile's loads (the job of the
+// reference's OS CTA: subscriber decode + scheduler doorbells, os/subscriber.cuh, os/scheduler.cuh -- here one warp, no queues).
+template <bool PAIR>
 __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, uint64_t* bars) {
-    uint64_t* sched_full = bars + 2 * STAGES + 4;
-    uint64_t* sched_empty = sched_full + NSCHED;
-    uint64_t* prod_take = sched_empty + NSCHED;
+    uint64_t* sched_full = bars + BAR_SCHED_FULL;
+    uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
+    uint64_t* prod_take = bars + BAR_PROD_TAKE;
     TileInfo* ring = reinterpret_cast<TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
+    const int mstep = PAIR ? 2 : 1;                         // row blocks per work item
+    const int tcm_items = (p.TCM + mstep - 1) / mstep;
     int q = 0, qphase = 0, cursor = 0, n = 0;
     for (;;) {
         int kind = -1;
@@ -440,15 +467,15 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 mbar_wait(&prod_take[pq], ((n - 1) / NSCHED) & 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, 200 + pq);
             }
             TileInfo ti;
-            ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows = 0; ti.src = 0; ti.le = 0; ti.bn = 0;
-            ti.nk = 0; ti.a_row = 0; ti.b_row = 0; ti.pad = 0;
+            ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows[0] = 0; ti.rows[1] = 0; ti.src = 0; ti.le = 0;
+            ti.bn = 0; ti.nk = 0; ti.a_row = 0; ti.b_row = 0; ti.pad[0] = ti.pad[1] = ti.pad[2] = ti.pad[3] = 0;
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
                 while (id >= p.blocks[cursor + 1].start) ++cursor;
                 const TileBlock blk = p.blocks[cursor];
                 const int local = id - blk.start;
-                const int mblk = local % p.TCM, nt = local / p.TCM;
+                const int mblk = (local % tcm_items) * mstep, nt = local / tcm_items;
                 const int src = blk.pkt / p.nLx, le = blk.pkt - src * p.nLx;
                 // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
                 unsigned long long f;
@@ -458,16 +485,21 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                         g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, blk.pkt, (unsigned int)(f >> 32), p.epoch);
                 }
                 const int cnt = (int)(f & 0xffffffffull);
-                if (mblk == 0 && nt == 0 && blk.kind == 0) p.recv_cnt[blk.pkt] = cnt;
-                if (mblk * BLOCK_M >= cnt) continue;  // empty row block of the static superset
-                if (blk.kind == 1) {  // GEMM1 needs the whole h row block (reference notifyNext, processor.cuh:490-615)
-                    SpinGuard g;
-                    const unsigned int* ctr = p.g0_done + (size_t)blk.pkt * p.TCM + mblk;
-                    while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
-                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, blk.pkt, mblk, 0);
+                if (local == 0 && blk.kind == 0) p.recv_cnt[blk.pkt] = cnt;
+                if (mblk * BLOCK_M >= cnt) continue;  // empty row block(s) of the static superset
+                const int rows0 = min(BLOCK_M, cnt - mblk * BLOCK_M);
+                const int rows1 = PAIR ? max(0, min(BLOCK_M, cnt - (mblk + 1) * BLOCK_M)) : 0;
+                if (blk.kind == 1) {  // GEMM1 needs whole h row blocks (reference notifyNext, processor.cuh:490-615)
+                    for (int r = 0; r < mstep; ++r) {
+                        if (r == 1 && rows1 == 0) break;
+                        SpinGuard g;
+                        const unsigned int* ctr = p.g0_done + (size_t)blk.pkt * p.TCM + mblk + r;
+                        while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, blk.pkt, mblk + r, 0);
+                    }
                 }
                 ti.kind = blk.kind; ti.pkt = blk.pkt; ti.mblk = mblk; ti.ntile = nt;
-                ti.rows = min(BLOCK_M, cnt - mblk * BLOCK_M);
+                ti.rows[0] = rows0; ti.rows[1] = rows1;
                 ti.src = src; ti.le = le;
                 ti.bn = p.bn[blk.kind];
                 ti.nk = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
@@ -480,6 +512,13 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
             if (ti.kind >= 0 && n < 48) trace_stamp(p, 16 + n);
             mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
             ring[q] = ti;
+            if (PAIR) {  // mirror the descriptor into the peer CTA's ring over DSMEM, then signal both rings
+                const uint4* src4 = reinterpret_cast<const uint4*>(&ti);
+                const uint32_t remote = mapa_shared(smem_u32(&ring[q]), 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st_shared_cluster_v4(remote + 16 * i, src4[i]);
+                mbar_arrive_cluster(&sched_full[q], 1);
+            }
             mbar_arrive(&sched_full[q]);
             kind = ti.kind;
         }
@@ -491,12 +530,16 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
     }
 }
 
-__device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, uint64_t* bars) {
-    uint64_t* full = bars;
-    uint64_t* empty = bars + STAGES;
-    uint64_t* sched_full = bars + 2 * STAGES + 4;
-    uint64_t* sched_empty = sched_full + NSCHED;
-    uint64_t* prod_take = sched_empty + NSCHED;
+// warp 0 of every CTA: TMA producer.  In pair mode each CTA loads its own A row block and its half of the B rows; all
+// completion bytes are credited to the leader's `full` barrier (the only one the MMA issuer waits on).
+template <bool PAIR>
+__device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t crank) {
+    using PC = PipeCfg<PAIR>;
+    uint64_t* full = bars + BAR_FULL;
+    uint64_t* empty = bars + BAR_EMPTY;
+    uint64_t* sched_full = bars + BAR_SCHED_FULL;
+    uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
+    uint64_t* prod_take = bars + BAR_PROD_TAKE;
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
     int stage = 0, phase = 0, q = 0, qphase = 0;
@@ -504,9 +547,9 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
         int kind = -1;
         TileInfo ti;
         if (lane == 0) {
-            mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, 300 + q);
+            wait_sched_full<PAIR>(p, &sched_full[q], qphase, 300 + q);
             ti = ring[q];
-            mbar_arrive(&sched_empty[q]);
+            release_to_leader<PAIR>(&sched_empty[q], crank);
             kind = ti.kind;
         }
         kind = __shfl_sync(0xffffffffu, kind, 0);
@@ -515,16 +558,27 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
             fence_proxy_async_global();  // rows written by generic-proxy stores (peers / other SMs) -> TMA reads
             const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
             const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
-            const uint32_t tx = (uint32_t)(A_STAGE_BYTES + ti.bn * BLOCK_K * 2);
+            const int b_rows = ti.bn / PC::B_ROWS_DIV;
+            const uint32_t tx_cta = (uint32_t)(A_STAGE_BYTES + b_rows * BLOCK_K * 2);
+            const int a_row = ti.a_row + (PAIR ? (int)crank * BLOCK_M : 0);
+            const int b_row = ti.b_row + (PAIR ? (int)crank * b_rows : 0);
             const int take_at = min(ti.nk - 1, max(0, ti.nk - p.claim_ahead_kb));
             for (int kb = 0; kb < ti.nk; ++kb) {
-                if (kb == take_at) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
+                if (kb == take_at && crank == 0) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
-                mbar_arrive_expect_tx(&full[stage], tx);
-                uint8_t* sa = smem + stage * STAGE_BYTES;
-                tma_load_2d(sa, ta, kb * BLOCK_K, ti.a_row, &full[stage]);
-                tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, ti.b_row, &full[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                uint8_t* sa = smem + stage * PC::STAGE_BYTES;
+                if (PAIR) {
+                    if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * tx_cta);
+                    else mbar_arrive_cluster(&full[stage], 0);
+                    const uint32_t leader_full = mapa_shared(smem_u32(&full[stage]), 0);
+                    tma_load_2d_pair(sa, ta, kb * BLOCK_K, a_row, leader_full);
+                    tma_load_2d_pair(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, leader_full);
+                } else {
+                    mbar_arrive_expect_tx(&full[stage], tx_cta);
+                    tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
+                    tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
+                }
+                if (++stage == PC::STAGES) { stage = 0; phase ^= 1; }
             }
         }
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
@@ -532,13 +586,16 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
     }
 }
 
+// warp 1 (leader CTA only in pair mode): the single thread that issues tcgen05.mma
+template <bool PAIR>
 __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base) {
-    uint64_t* full = bars;
-    uint64_t* empty = bars + STAGES;
-    uint64_t* tmem_full = bars + 2 * STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* sched_full = bars + 2 * STAGES + 4;
-    uint64_t* sched_empty = sched_full + NSCHED;
+    using PC = PipeCfg<PAIR>;
+    uint64_t* full = bars + BAR_FULL;
+    uint64_t* empty = bars + BAR_EMPTY;
+    uint64_t* tmem_full = bars + BAR_TMEM_FULL;
+    uint64_t* tmem_empty = bars + BAR_TMEM_EMPTY;
+    uint64_t* sched_full = bars + BAR_SCHED_FULL;
+    uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
     int stage = 0, phase = 0, q = 0, qphase = 0, as = 0, aphase = 0;
@@ -555,26 +612,30 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         if (kind < 0) break;
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(BLOCK_M, (uint32_t)bn);
+            const uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, (uint32_t)bn);
             mbar_wait(&tmem_empty[as], aphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_EMPTY, as);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)as * BLOCK_N;
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait(&full[stage], phase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, stage);
                 tcgen05_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                const uint32_t sa = smem_u32(smem + stage * PC::STAGE_BYTES);
                 const uint64_t da = umma_smem_desc_sw128(sa);
                 const uint64_t db = umma_smem_desc_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                     // +32 bytes per UMMA_K step inside the 128-byte swizzle row (address field is in 16-byte units)
-                    umma_bf16_ss(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
-                                 (kb | kk) != 0 ? 1u : 0u);
+                    if (PAIR) umma_bf16_ss_pair(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                                                (kb | kk) != 0 ? 1u : 0u);
+                    else umma_bf16_ss(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc,
+                                      (kb | kk) != 0 ? 1u : 0u);
                 }
-                umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                // smem slot reusable once these MMAs have read it (pair: signalled to both CTAs' producers)
+                if (PAIR) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+                if (++stage == PC::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&tmem_full[as]);     // accumulator complete -> epilogue
+            // accumulator complete -> epilogue warps (of both CTAs in pair mode)
+            if (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
         __syncwarp();
@@ -586,36 +647,42 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));             // GELU, erf form
 }
 
-__device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base) {
-    uint64_t* tmem_full = bars + 2 * STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* sched_full = bars + 2 * STAGES + 4;
-    uint64_t* sched_empty = sched_full + NSCHED;
+// warps 4-7 of every CTA: TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced global / peer stores
+template <bool PAIR>
+__device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base,
+                                             uint32_t crank) {
+    uint64_t* tmem_full = bars + BAR_TMEM_FULL;
+    uint64_t* tmem_empty = bars + BAR_TMEM_EMPTY;
+    uint64_t* sched_full = bars + BAR_SCHED_FULL;
+    uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
     uint8_t* stg = smem + OFF_EPI + quarter * EPI_WARP_BYTES;
     int q = 0, qphase = 0, as = 0, aphase = 0, ntiles = 0;
     for (;;) {
-        mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, 100 + q);
+        wait_sched_full<PAIR>(p, &sched_full[q], qphase, 100 + q);
         const TileInfo ti = ring[q];
-        mbar_arrive(&sched_empty[q]);
+        __syncwarp();
+        if (lane == 0) release_to_leader<PAIR>(&sched_empty[q], crank);
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         if (ti.kind < 0) break;
         const int N = ti.kind == 0 ? p.P : p.H;
         const int n0 = ti.ntile * ti.bn;
+        const int my_rows = ti.rows[PAIR ? crank : 0];
+        const int my_mblk = ti.mblk + (PAIR ? (int)crank : 0);
         const __nv_bfloat16* bias = ti.kind == 0 ? (p.b_up ? p.b_up + (size_t)ti.le * p.P : nullptr)
                                                  : (p.b_down ? p.b_down + (size_t)ti.le * p.H : nullptr);
         // destination rows: GEMM0 -> local h staging; GEMM1 -> the SOURCE rank's return buffer (peer store),
         // like the reference's GEMM1 epilogue writing into the peer heap (packet.cuh:338-340, processor.cuh:713-720)
         __nv_bfloat16* out_rows;
         if (ti.kind == 0) {
-            out_rows = p.hidden + ((size_t)ti.pkt * p.pEC + (size_t)ti.mblk * BLOCK_M) * p.P;
+            out_rows = p.hidden + ((size_t)ti.pkt * p.pEC + (size_t)my_mblk * BLOCK_M) * p.P;
         } else {
             const int e_global = p.rank * p.nLx + ti.le;
-            out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)ti.mblk * BLOCK_M) * p.H;
+            out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)my_mblk * BLOCK_M) * p.H;
         }
-        const int nchunks = min(ti.bn / 64, (N - n0) / 64);
+        const int nchunks = my_rows > 0 ? min(ti.bn / 64, (N - n0) / 64) : 0;
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
@@ -625,9 +692,10 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             tmem_ld_32x32b_x32(t_row + c * 64, v0);
             tmem_ld_32x32b_x32(t_row + c * 64 + 32, v1);
             tmem_ld_wait();
-            if (c == nchunks - 1) {  // last TMEM read of this accumulator: hand it back to the MMA warp
+            if (c == nchunks - 1) {  // last TMEM read of this accumulator: hand it back to the MMA issuer
                 tcgen05_fence_before();
-                mbar_arrive(&tmem_empty[as]);
+                __syncwarp();
+                if (lane == 0) release_to_leader<PAIR>(&tmem_empty[as], crank);
             }
             float bv[8];
             uint8_t* my_row = stg + lane * EPI_ROW_BYTES;
@@ -660,14 +728,15 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
                 const int r = it * 4 + (lane >> 3), seg = lane & 7;
                 const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_ROW_BYTES + seg * 16);
                 const int row_in_tile = quarter * 32 + r;
-                if (row_in_tile < ti.rows)
+                if (row_in_tile < my_rows)
                     st_global_v4(out_rows + (size_t)row_in_tile * N + n0 + c * 64 + seg * 8, o);
             }
             __syncwarp();
         }
-        if (nchunks <= 0) {  // cannot happen (N % 64 == 0 and n0 < N) but never leave the accumulator unreleased
+        if (nchunks <= 0) {  // nothing to drain (row block past the packet's rows): still release the accumulator
             tcgen05_fence_before();
-            mbar_arrive(&tmem_empty[as]);
+            __syncwarp();
+            if (lane == 0) release_to_leader<PAIR>(&tmem_empty[as], crank);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
 
@@ -677,21 +746,67 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         if (tid == EPI_WARP0 * 32) {
             if (ntiles < 48) trace_stamp(p, 64 + ntiles);
             ++ntiles;
-            if (ti.kind == 0) {
-                fence_proxy_async_global();
-                red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + ti.mblk, 1u);
-            } else {
-                fence_acq_rel_sys();
-                const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + ti.mblk, 1u);
-                if (old == (unsigned int)p.TN1 - 1u) {  // whole rows of this block are on the source rank
+            if (my_rows > 0) {
+                if (ti.kind == 0) {
+                    fence_proxy_async_global();
+                    red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                } else {
                     fence_acq_rel_sys();
-                    const int e_global = p.rank * p.nLx + ti.le;
-                    st_release_sys_u64(p.peer_ret_flag[ti.src] + (size_t)e_global * p.TCM + ti.mblk,
-                                       ((unsigned long long)p.epoch << 32) | (unsigned int)ti.rows);
+                    const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                    if (old == (unsigned int)p.TN1 - 1u) {  // whole rows of this block are on the source rank
+                        fence_acq_rel_sys();
+                        const int e_global = p.rank * p.nLx + ti.le;
+                        st_release_sys_u64(p.peer_ret_flag[ti.src] + (size_t)e_global * p.TCM + my_mblk,
+                                           ((unsigned long long)p.epoch << 32) | (unsigned int)my_rows);
+                    }
                 }
             }
         }
     }
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void ffn_phase(const FmParams& p, uint8_t* smem) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    if (warp == 1 && (tid & 31) == 0) {
+        // arrival counts: full = leader's expect_tx (+ the peer producer's arrive); empty / tmem_full = one tcgen05.commit;
+        // tmem_empty = one lane per epilogue warp (of both CTAs); sched_empty = producer(s) + MMA lane + epilogue warps
+        const int nc = PAIR ? 2 : 1;
+        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[BAR_FULL + i], nc); mbar_init(&bars[BAR_EMPTY + i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[BAR_TMEM_FULL + i], 1); mbar_init(&bars[BAR_TMEM_EMPTY + i], 4 * nc); }
+        for (int i = 0; i < NSCHED; ++i) {
+            mbar_init(&bars[BAR_SCHED_FULL + i], 1);
+            mbar_init(&bars[BAR_SCHED_EMPTY + i], 1 + 5 * nc);
+            mbar_init(&bars[BAR_PROD_TAKE + i], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 0 && (tid & 31) == 0) {
+        tma_prefetch_desc(&p.tm_a0); tma_prefetch_desc(&p.tm_b0);
+        tma_prefetch_desc(&p.tm_a1); tma_prefetch_desc(&p.tm_b1);
+    }
+    if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
+    tcgen05_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised before any remote arrive
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (tid == 0) trace_stamp(p, 4);
+    if (warp == 0) ffn_producer<PAIR>(p, smem, bars, crank);
+    else if (warp == 1) { if (crank == 0) ffn_mma<PAIR>(p, smem, bars, tmem_base); }
+    else if (warp == 3) { if (crank == 0) ffn_scheduler<PAIR>(p, smem, bars); }
+    else if (warp >= EPI_WARP0) ffn_epilogue<PAIR>(p, smem, bars, tmem_base, crank);
+
+    tcgen05_fence_before();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // nobody leaves while the partner may still touch its smem/TMEM
+    if (warp == 2) {
+        tcgen05_fence_after();
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+    if (tid == 0) trace_stamp(p, 5);
 }
 
 // ============================================================================================================
@@ -807,12 +922,11 @@ __device__ __forceinline__ void combine_phase(const FmParams& p, uint8_t* smem, 
 }
 
 // ============================================================================================================
+template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __grid_constant__ FmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int t0 = blockIdx.x * p.tpc;
     const int n_tok = max(0, min(p.tpc, p.S - t0));
 
@@ -840,49 +954,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
     }
     __syncthreads();
 
-    if (p.phase_mask & 2u) {
-        if (warp == 1 && (tid & 31) == 0) {
-            uint64_t* full = bars;
-            uint64_t* empty = bars + STAGES;
-            uint64_t* tmem_full = bars + 2 * STAGES;
-            uint64_t* tmem_empty = tmem_full + 2;
-            uint64_t* sched_full = bars + 2 * STAGES + 4;
-            uint64_t* sched_empty = sched_full + NSCHED;
-            for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
-            uint64_t* prod_take = sched_empty + NSCHED;
-            for (int i = 0; i < NSCHED; ++i) {
-                mbar_init(&sched_full[i], 1);
-                mbar_init(&sched_empty[i], 130);  // producer + MMA lane + 128 epilogue threads
-                mbar_init(&prod_take[i], 1);
-            }
-            fence_mbar_init();
-        }
-        if (warp == 0 && (tid & 31) == 0) {
-            tma_prefetch_desc(&p.tm_a0); tma_prefetch_desc(&p.tm_b0);
-            tma_prefetch_desc(&p.tm_a1); tma_prefetch_desc(&p.tm_b1);
-        }
-        if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
-        tcgen05_fence_before();
-        __syncthreads();
-        tcgen05_fence_after();
-        const uint32_t tmem_base = *tmem_ptr;
+    if (p.phase_mask & 2u) ffn_phase<PAIR>(p, smem);
 
-        if (tid == 0) trace_stamp(p, 4);
-        if (warp == 0) ffn_producer(p, smem, bars);
-        else if (warp == 1) ffn_mma(p, smem, bars, tmem_base);
-        else if (warp == 3) ffn_scheduler(p, smem, bars);
-        else if (warp >= EPI_WARP0) ffn_epilogue(p, smem, bars, tmem_base);
-
-        tcgen05_fence_before();
-        __syncthreads();
-        if (warp == 2) {
-            tcgen05_fence_after();
-            tmem_dealloc(tmem_base, TMEM_COLS);
-        }
-        if (tid == 0) trace_stamp(p, 5);
-    }
     if (p.phase_mask & 4u) {
+        __syncthreads();
         combine_phase(p, smem, t0, n_tok);
         __syncthreads();
         if (tid == 0) trace_stamp(p, 6);
