@@ -472,6 +472,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
+                if (n < 16) trace_stamp(p, 112 + n);   // claim time of tile n (ready time is slot 16+n)
                 while (id >= p.blocks[cursor + 1].start) ++cursor;
                 const TileBlock blk = p.blocks[cursor];
                 const int local = id - blk.start;

@@ -134,6 +134,26 @@ def stage(args):
         last_done = np.array([done[c, ntiles[c]-1] if ntiles[c] else tr[c,4] for c in range(tr.shape[0])])
         v = (last_done - t00) / 1e3
         print(f"  last tile stored: min {v.min():.1f} med {np.median(v):.1f} max {v.max():.1f} us")
+        claim = tr[:, 112:128]
+        stall = []; gap = []; busy = []; span = []
+        for c in range(tr.shape[0]):
+            n = int(ntiles[c])
+            if n == 0: continue
+            for i in range(min(n, 16)):
+                if claim[c, i] > 0: stall.append((ready[c, i] - claim[c, i]) / 1e3)
+            b = 0.0
+            for i in range(n):
+                prev_done = done[c, i - 1] if i > 0 else tr[c, 4]
+                b += (done[c, i] - max(prev_done, ready[c, i])) / 1e3
+                if i > 0: gap.append(max(0, ready[c, i] - done[c, i - 1]) / 1e3)
+            busy.append(b); span.append((done[c, n - 1] - tr[c, 4]) / 1e3)
+        stall = np.array(stall); gap = np.array(gap); busy = np.array(busy); span = np.array(span)
+        print(f"  claim->ready stall (us): med {np.median(stall):.2f} p90 {np.percentile(stall,90):.2f} max {stall.max():.2f} sum/CTA {stall.sum()/len(busy):.1f}")
+        print(f"  ready after previous tile stored (exposed gap, us): med {np.median(gap):.2f} p90 {np.percentile(gap,90):.2f} max {gap.max():.2f}")
+        print(f"  per-CTA busy med {np.median(busy):.1f} span med {np.median(span):.1f} max {span.max():.1f}; sum busy / (max span * CTAs) = {busy.sum()/(span.max()*len(busy)):.3f}")
+        k0 = [ (done[c,i]-max(done[c,i-1] if i>0 else tr[c,4], ready[c,i]))/1e3 for c in range(tr.shape[0]) for i in range(int(ntiles[c]))]
+        k0 = np.array(k0); short = k0[k0 < 15]; long_ = k0[k0 >= 15]
+        if len(short) and len(long_): print(f"  short tiles n={len(short)} mean {short.mean():.2f} us; long tiles n={len(long_)} mean {long_.mean():.2f} us")
         np.save("gpurun_out/trace_%s.npy" % args.cfg, tr)
     ctx.close()
 
