@@ -128,6 +128,9 @@ struct fm_ctx {
     void* symm = nullptr;
     bool symm_external = false;
     size_t symm_bytes = 0, off_recv_x = 0, off_ret_y = 0, off_recv_flag = 0, off_ret_flag = 0;
+    size_t off_recv_meta = 0, off_out_acc = 0, off_done_flag = 0;
+    bool fused = false;   // GEMM1 epilogue adds straight into the source rank's output (no return buffer / gather)
+    unsigned int* pkt_done = nullptr;
     void* peer_base[FM_MAX_WORLD] = {};
     bool peer_opened[FM_MAX_WORLD] = {};
     bool attached = false;
@@ -200,6 +203,9 @@ void set_peer_pointers(const fm_ctx* c, fm::FmParams& p) {
         p.peer_ret_y[r] = reinterpret_cast<__nv_bfloat16*>(b + c->off_ret_y);
         p.peer_recv_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_recv_flag);
         p.peer_ret_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_ret_flag);
+        p.peer_recv_meta[r] = reinterpret_cast<uint4*>(b + c->off_recv_meta);
+        p.peer_done_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_done_flag);
+        p.peer_out_acc[r] = reinterpret_cast<__nv_bfloat16*>(b + c->off_out_acc);
     }
 }
 
@@ -282,6 +288,13 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.recv_flag = reinterpret_cast<unsigned long long*>(sb + c->off_recv_flag);
     p.ret_flag = reinterpret_cast<unsigned long long*>(sb + c->off_ret_flag);
     set_peer_pointers(c, p);
+    p.fused = c->fused ? 1 : 0;
+    p.pkt_done = c->pkt_done;
+    p.recv_meta = reinterpret_cast<uint4*>(sb + c->off_recv_meta);
+    p.done_flag = reinterpret_cast<unsigned long long*>(sb + c->off_done_flag);
+    // single rank: accumulate straight into the caller's tensor; otherwise into the peer-mapped accumulator
+    p.out_acc = d.world == 1 ? p.out : reinterpret_cast<__nv_bfloat16*>(sb + c->off_out_acc);
+    if (d.world == 1) p.peer_out_acc[0] = p.out;
     p.dbg = c->dbg_dev;
     p.trace = c->trace_on ? c->trace : nullptr;
 
@@ -384,6 +397,8 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     {
         const char* v = getenv("FM_PAIR");
         ctx->pair = (v != nullptr && *v) ? atoi(v) != 0 : false;
+        const char* f = getenv("FM_FUSED_COMBINE");
+        ctx->fused = (f != nullptr && *f) ? atoi(f) != 0 : false;
         if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
     }
     ctx->tpc = ceil_div(d.S, ctx->grid);
@@ -463,6 +478,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     FM_TRY(dev_alloc(&ctx->g0_done, (size_t)ctx->num_pkts * d.TCM));
     FM_TRY(dev_alloc(&ctx->g1_done, (size_t)ctx->num_pkts * d.TCM));
     FM_TRY(dev_alloc(&ctx->recv_cnt, (size_t)ctx->num_pkts));
+    FM_TRY(dev_alloc(&ctx->pkt_done, (size_t)ctx->num_pkts));
     FM_TRY(dev_alloc(&ctx->blocks, blocks.size(), false));
     FM_TRY_CUDA(cudaMemcpy(ctx->blocks, blocks.data(), blocks.size() * sizeof(fm::TileBlock), cudaMemcpyHostToDevice));
     FM_TRY(dev_alloc(&ctx->hidden, (size_t)ctx->num_pkts * d.pEC * d.P));
@@ -474,6 +490,9 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->off_ret_y = off;  off = align_up(off + (size_t)d.E * d.pEC * d.H * 2, 1024);
     ctx->off_recv_flag = off; off = align_up(off + (size_t)ctx->num_pkts * 8, 1024);
     ctx->off_ret_flag = off;  off = align_up(off + (size_t)d.E * d.TCM * 8, 1024);
+    ctx->off_recv_meta = off; off = align_up(off + (size_t)ctx->num_pkts * d.pEC * 16, 1024);
+    ctx->off_done_flag = off; off = align_up(off + (size_t)d.E * 8, 1024);
+    ctx->off_out_acc = off;   off = align_up(off + (world > 1 ? (size_t)d.S * d.H * 2 : 0), 1024);
     ctx->symm_bytes = off;
     {
         void* q = nullptr;
@@ -506,7 +525,7 @@ FM_API int fm_destroy(fm_ctx_t* ctx) {
     for (int r = 0; r < ctx->d.world; ++r)
         if (ctx->peer_opened[r] && ctx->peer_base[r] != nullptr) cudaIpcCloseMemHandle(ctx->peer_base[r]);
     void* bufs[] = {ctx->topk_idx, ctx->topk_w, ctx->mcw, ctx->slot, ctx->counts, ctx->gate_out, ctx->chunk_counts,
-                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace, ctx->x_stage,
+                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->pkt_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace, ctx->x_stage,
                     ctx->out_stage};
     for (void* b : bufs)
         if (b != nullptr) cudaFree(b);

@@ -116,6 +116,16 @@ struct FmParams {
     unsigned long long* peer_recv_flag[FM_MAX_WORLD];
     __nv_bfloat16* peer_ret_y[FM_MAX_WORLD];
     unsigned long long* peer_ret_flag[FM_MAX_WORLD];
+    // fused GEMM1 -> combine path (fused != 0): the GEMM1 epilogue scales each row and adds it straight into the
+    // source rank's output rows (peer REDG over NVLink); no return buffer, no per-row-block flags, no gather pass
+    int fused;
+    unsigned int* pkt_done;            // [num_pkts] GEMM1 tiles finished per packet
+    uint4* recv_meta;                  // local symmetric [W*nLx*pEC] {token, p~ (f32 bits), mCw (f32 bits), 0}
+    unsigned long long* done_flag;     // local symmetric [E] {epoch, 0}: expert e's contributions to my tokens are all in
+    __nv_bfloat16* out_acc;            // my accumulation target: caller's out (W == 1) or the symmetric out buffer
+    uint4* peer_recv_meta[FM_MAX_WORLD];
+    unsigned long long* peer_done_flag[FM_MAX_WORLD];
+    __nv_bfloat16* peer_out_acc[FM_MAX_WORLD];
     DebugRecord* dbg;
     unsigned long long* trace;  // optional [grid][TRACE_SLOTS] %globaltimer stamps (nullptr = off)
 };
@@ -308,6 +318,13 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         __syncthreads();
     }
     if (tid == 0) trace_stamp(p, 12);
+    if (p.fused) {   // accumulation target rows start at zero (reference clearState zeroes the output, moe.cuh:43-48)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
+            __nv_bfloat16* row = p.out_acc + (size_t)(t0 + ti) * H;
+            for (int h = lane * 8; h < H; h += 256) st_global_v4(row + h, z);
+        }
+    }
     // position of every (token, pick) among this chunk's selections of the same expert, ascending token order
     for (int e = tid; e < E; e += NUM_THREADS) {
         int cnt = 0;
@@ -362,6 +379,14 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
                 if (lane == 0) p.slot[(size_t)t * k + j] = s;
                 keep[j] = s < p.EC;
                 const int owner = e / p.nLx, le = e - owner * p.nLx;
+                if (p.fused && lane == 0 && keep[j]) {   // what the expert's GEMM1 epilogue needs to combine this row
+                    uint4 m;
+                    m.x = (unsigned int)t;
+                    m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
+                    m.z = __float_as_uint(p.mcw[t]);
+                    m.w = 0u;
+                    st_global_v4(p.peer_recv_meta[owner] + (size_t)(p.rank * p.nLx + le) * p.pEC + s, m);
+                }
                 dst[j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[j] ? s : 0)) * H;
             }
         }
@@ -430,7 +455,8 @@ struct TileInfo {     // 64 bytes, written by the (leader's) scheduler warp, rea
     int nk;           // k-blocks
     int a_row;        // TMA row coordinate of rank 0's A tile (rank 1: + 128)
     int b_row;        // TMA row coordinate of the B tile (rank 1 of a pair: + bn/2)
-    int pad[4];
+    int cnt;          // rows of the whole packet
+    int pad[3];
 };
 static_assert(sizeof(TileInfo) == 64, "TileInfo must be 4 x 16 bytes");
 
@@ -468,7 +494,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
             }
             TileInfo ti;
             ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows[0] = 0; ti.rows[1] = 0; ti.src = 0; ti.le = 0;
-            ti.bn = 0; ti.nk = 0; ti.a_row = 0; ti.b_row = 0; ti.pad[0] = ti.pad[1] = ti.pad[2] = ti.pad[3] = 0;
+            ti.bn = 0; ti.nk = 0; ti.a_row = 0; ti.b_row = 0; ti.cnt = 0; ti.pad[0] = ti.pad[1] = ti.pad[2] = 0;
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
@@ -487,6 +513,9 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 }
                 const int cnt = (int)(f & 0xffffffffull);
                 if (local == 0 && blk.kind == 0) p.recv_cnt[blk.pkt] = cnt;
+                if (p.fused && local == 0 && blk.kind == 1 && cnt == 0)   // nothing to contribute: tell the source now
+                    st_release_sys_u64(p.peer_done_flag[src] + (size_t)(p.rank * p.nLx + le),
+                                       (unsigned long long)p.epoch << 32);
                 if (mblk * BLOCK_M >= cnt) continue;  // empty row block(s) of the static superset
                 const int rows0 = min(BLOCK_M, cnt - mblk * BLOCK_M);
                 const int rows1 = PAIR ? max(0, min(BLOCK_M, cnt - (mblk + 1) * BLOCK_M)) : 0;
@@ -501,7 +530,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 }
                 ti.kind = blk.kind; ti.pkt = blk.pkt; ti.mblk = mblk; ti.ntile = nt;
                 ti.rows[0] = rows0; ti.rows[1] = rows1;
-                ti.src = src; ti.le = le;
+                ti.src = src; ti.le = le; ti.cnt = cnt;
                 ti.bn = p.bn[blk.kind];
                 ti.nk = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
                 ti.a_row = blk.pkt * p.pEC + mblk * BLOCK_M;
@@ -684,6 +713,17 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)my_mblk * BLOCK_M) * p.H;
         }
         const int nchunks = my_rows > 0 ? min(ti.bn / 64, (N - n0) / 64) : 0;
+        // fused GEMM1 -> combine: this thread owns accumulator row (quarter*32 + lane); fetch that row's routing record
+        const bool fuse = p.fused != 0 && ti.kind == 1;
+        int my_tok = 0;
+        float my_pw = 0.0f, my_mcw = 1.0f;
+        if (fuse && quarter * 32 + lane < my_rows) {
+            const uint4 m = ld_global_v4(p.recv_meta + (size_t)ti.pkt * p.pEC + (size_t)my_mblk * BLOCK_M + quarter * 32 + lane);
+            my_tok = (int)m.x;
+            my_pw = __uint_as_float(m.y);
+            my_mcw = __uint_as_float(m.z);
+        }
+        __nv_bfloat16* acc_base = fuse ? p.peer_out_acc[ti.src] : nullptr;
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
@@ -716,6 +756,11 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
                 if (ti.kind == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) f[i] = apply_act(f[i], p.act);
+                } else if (fuse && p.k > 1) {
+                    // the reference's combine arithmetic on the bf16-rounded y (processor.cuh:110-169):
+                    // term = rne( p~ (x) rne( y / mCw ) ); the bf16 accumulation itself is the REDG below
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = my_pw * rne_bf16(__fdividef(rne_bf16(f[i]), my_mcw));
                 }
                 uint4 o;
                 o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
@@ -729,8 +774,15 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
                 const int r = it * 4 + (lane >> 3), seg = lane & 7;
                 const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_ROW_BYTES + seg * 16);
                 const int row_in_tile = quarter * 32 + r;
-                if (row_in_tile < my_rows)
+                if (fuse) {   // row -> its token's output row on the source rank (k == 1: plain copy, reference :170-203)
+                    const int tok = __shfl_sync(0xffffffffu, my_tok, r);
+                    if (row_in_tile < my_rows) {
+                        __nv_bfloat16* dst = acc_base + (size_t)tok * N + n0 + c * 64 + seg * 8;
+                        if (p.k > 1) red_add_bf16x8(dst, o); else st_global_v4(dst, o);
+                    }
+                } else if (row_in_tile < my_rows) {
                     st_global_v4(out_rows + (size_t)row_in_tile * N + n0 + c * 64 + seg * 8, o);
+                }
             }
             __syncwarp();
         }
@@ -751,6 +803,15 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
                 if (ti.kind == 0) {
                     fence_proxy_async_global();
                     red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                } else if (fuse) {
+                    fence_acq_rel_sys();   // this tile's adds are performed before the packet counter moves
+                    const unsigned int old = atom_acq_rel_gpu_add_u32(p.pkt_done + ti.pkt, 1u);
+                    const unsigned int want = (unsigned int)(((ti.cnt + BLOCK_M - 1) / BLOCK_M) * p.TN1);
+                    if (old + 1u == want) {   // every GEMM1 tile of packet (src, le) has been added into src's output
+                        fence_acq_rel_sys();
+                        st_release_sys_u64(p.peer_done_flag[ti.src] + (size_t)(p.rank * p.nLx + ti.le),
+                                           (unsigned long long)p.epoch << 32);
+                    }
                 } else {
                     fence_acq_rel_sys();
                     const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
@@ -878,6 +939,37 @@ __device__ __forceinline__ void combine_rows(const FmParams& p, int t0, int n_to
     }
 }
 
+// fused path: the output rows were accumulated by the GEMM1 epilogues; wait until every expert (local or remote) has
+// reported all of its contributions, then (W > 1) move my rows from the symmetric accumulator to the caller's tensor
+__device__ __forceinline__ void finish_fused(const FmParams& p, int t0, int n_tok) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int e = tid; e < p.E; e += NUM_THREADS) {
+        SpinGuard g;
+        while ((ld_acquire_sys_u64(p.done_flag + e) >> 32) != p.epoch)
+            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RET_FLAG, e, 0xD0E, 0);
+    }
+    __syncthreads();
+    if (p.out_acc != p.out) {
+        for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
+            const __nv_bfloat16* src = p.out_acc + (size_t)(t0 + ti) * p.H;
+            __nv_bfloat16* dst = p.out + (size_t)(t0 + ti) * p.H;
+            for (int hg = 0; hg < p.H; hg += 1024) {
+                uint4 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int h = hg + i * 256 + lane * 8;
+                    if (h < p.H) v[i] = ld_global_v4(src + h);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int h = hg + i * 256 + lane * 8;
+                    if (h < p.H) st_global_v4(dst + h, v[i]);
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void combine_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, k = p.k;
@@ -938,6 +1030,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
                 p.g0_done[i] = 0u;
                 p.g1_done[i] = 0u;
             }
+            for (int i = tid; i < p.num_pkts; i += NUM_THREADS) p.pkt_done[i] = 0u;
             if (tid == 0) {
                 *p.claim = 0u;
                 *p.disp_done = 0u;
@@ -959,7 +1052,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
 
     if (p.phase_mask & 4u) {
         __syncthreads();
-        combine_phase(p, smem, t0, n_tok);
+        if (p.fused) finish_fused(p, t0, n_tok);
+        else combine_phase(p, smem, t0, n_tok);
         __syncthreads();
         if (tid == 0) trace_stamp(p, 6);
     }

@@ -177,6 +177,14 @@ __device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
                  : "memory");
 }
 
+// 8 x bf16 element-wise add into global memory (REDG.E.ADD.BF16x8.RN): round-to-nearest-even like a bf16 atomicAdd,
+// no return value; valid on peer-mapped addresses (NVLink atomics)
+__device__ __forceinline__ void red_add_bf16x8(void* p, const uint4& v) {
+    asm volatile("red.relaxed.sys.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------------------------
 // TMA: 2-D tiled bulk tensor load, global -> shared, completion on an mbarrier (complete_tx::bytes)
 // ----------------------------------------------------------------------------------------------------------------
