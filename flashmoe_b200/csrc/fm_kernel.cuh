@@ -200,6 +200,21 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             for (int hc0 = 0; hc0 < H; hc0 += Hc) {
                 const int hc_len = min(Hc, H - hc0);
                 __syncthreads();  // previous users of wg_s are done (also orders the logit_s zero fill)
+                const bool single = hc_len <= 1024;
+                uint4 xv[4][4];
+                // the first token block's x rows (HBM) are requested BEFORE Wg is staged, so both latencies overlap
+                if (single && warp * 4 < n_sub) {
+                    const int ntk0 = min(4, n_sub - warp * 4);
+                    const __nv_bfloat16* xr0 = p.x + (size_t)(t0 + s0 + warp * 4) * H + hc0;
+#pragma unroll
+                    for (int tk = 0; tk < 4; ++tk)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int h = i * 256 + lane * 8;
+                            xv[tk][i] = (tk < ntk0 && h < hc_len) ? ld_global_nc_v4(xr0 + (size_t)tk * H + h)
+                                                                  : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                }
                 // stage Wg_eff[eg0 .. eg0+eg_len, hc0 .. hc0+hc_len) -> wg_s[e][Hc], 16 B per thread-iteration
                 const int vec_per_row = hc_len >> 3;
                 for (int i = tid; i < eg_len * vec_per_row; i += NUM_THREADS) {
@@ -214,9 +229,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 for (int tb = warp * 4; tb < n_sub; tb += NUM_WARPS * 4) {
                     const int ntk = min(4, n_sub - tb);
                     const __nv_bfloat16* xr = p.x + (size_t)(t0 + s0 + tb) * H + hc0;
-                    const bool single = hc_len <= 1024;
-                    uint4 xv[4][4];
-                    if (single) {
+                    if (single && tb != warp * 4) {
 #pragma unroll
                         for (int tk = 0; tk < 4; ++tk)
 #pragma unroll
@@ -325,13 +338,21 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             for (int h = lane * 8; h < H; h += 256) st_global_v4(row + h, z);
         }
     }
-    // position of every (token, pick) among this chunk's selections of the same expert, ascending token order
-    for (int e = tid; e < E; e += NUM_THREADS) {
-        int cnt = 0;
-        for (int i = 0; i < n_tok * k; ++i)
-            if (sel_e[i] == e) rank_s[i] = cnt++;
-        p.chunk_counts[(size_t)blockIdx.x * E + e] = cnt;
+    // position of every (token, pick) among this chunk's selections of the same expert, ascending token order:
+    // one thread per entry counts the equal selections before it (warp-broadcast smem reads); totals by smem atomics
+    int* cnt_s = reinterpret_cast<int*>(smem + G_OFF_BASE);
+    for (int e = tid; e < E; e += NUM_THREADS) cnt_s[e] = 0;
+    __syncthreads();
+    const int n_ent = n_tok * k;
+    for (int i = tid; i < n_ent; i += NUM_THREADS) {
+        const int16_t e = sel_e[i];
+        int r = 0;
+        for (int j = 0; j < i; ++j) r += (sel_e[j] == e) ? 1 : 0;
+        rank_s[i] = r;
+        atomicAdd(&cnt_s[e], 1);
     }
+    __syncthreads();
+    for (int e = tid; e < E; e += NUM_THREADS) p.chunk_counts[(size_t)blockIdx.x * E + e] = cnt_s[e];
 }
 
 // ============================================================================================================
@@ -365,48 +386,55 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     }
     __syncthreads();
     if (tid == 0) trace_stamp(p, 8);
-    for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
-        const int t = t0 + ti;
-        __nv_bfloat16* dst[8];
-        bool keep[8];
+    for (int tp = warp * 2; tp < n_tok; tp += NUM_WARPS * 2) {   // two token rows in flight per warp
+        __nv_bfloat16* dst[2][8];
+        bool keep[2][8];
+        const int nt2 = min(2, n_tok - tp);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            keep[j] = false;
-            dst[j] = nullptr;
-            if (j < k) {
-                const int e = sel_e[ti * k + j];
-                const int s = base_s[e] + rank_s[ti * k + j];
-                if (lane == 0) p.slot[(size_t)t * k + j] = s;
-                keep[j] = s < p.EC;
-                const int owner = e / p.nLx, le = e - owner * p.nLx;
-                if (p.fused && lane == 0 && keep[j]) {   // what the expert's GEMM1 epilogue needs to combine this row
-                    uint4 m;
-                    m.x = (unsigned int)t;
-                    m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
-                    m.z = __float_as_uint(p.mcw[t]);
-                    m.w = 0u;
-                    st_global_v4(p.peer_recv_meta[owner] + (size_t)(p.rank * p.nLx + le) * p.pEC + s, m);
+        for (int u = 0; u < 2; ++u) {
+            const int ti = tp + u, t = t0 + ti;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                keep[u][j] = false;
+                dst[u][j] = nullptr;
+                if (u < nt2 && j < k) {
+                    const int e = sel_e[ti * k + j];
+                    const int s = base_s[e] + rank_s[ti * k + j];
+                    if (lane == 0) p.slot[(size_t)t * k + j] = s;
+                    keep[u][j] = s < p.EC;
+                    const int owner = e / p.nLx, le = e - owner * p.nLx;
+                    if (p.fused && lane == 0 && keep[u][j]) {   // what the expert's GEMM1 epilogue needs to combine this row
+                        uint4 m;
+                        m.x = (unsigned int)t;
+                        m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
+                        m.z = __float_as_uint(p.mcw[t]);
+                        m.w = 0u;
+                        st_global_v4(p.peer_recv_meta[owner] + (size_t)(p.rank * p.nLx + le) * p.pEC + s, m);
+                    }
+                    dst[u][j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[u][j] ? s : 0)) * H;
                 }
-                dst[j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[j] ? s : 0)) * H;
             }
         }
-        const __nv_bfloat16* src = p.x + (size_t)t * H;
         for (int hg = 0; hg < H; hg += 1024) {
-            uint4 v[4];
+            uint4 v[2][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = hg + i * 256 + lane * 8;
-                if (h < H) v[i] = ld_global_nc_v4(src + h);
-            }
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = hg + i * 256 + lane * 8;
-                if (h < H) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < k && keep[j]) st_global_v4(dst[j] + h, v[i]);
+                for (int i = 0; i < 4; ++i) {
+                    const int h = hg + i * 256 + lane * 8;
+                    if (u < nt2 && h < H) v[u][i] = ld_global_nc_v4(p.x + (size_t)(t0 + tp + u) * H + h);
                 }
-            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int h = hg + i * 256 + lane * 8;
+                    if (u < nt2 && h < H) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (j < k && keep[u][j]) st_global_v4(dst[u][j] + h, v[u][i]);
+                    }
+                }
         }
     }
     __syncthreads();
