@@ -397,8 +397,11 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     {
         const char* v = getenv("FM_PAIR");
         ctx->pair = (v != nullptr && *v) ? atoi(v) != 0 : false;
+        // fused GEMM1 -> combine (REDG into the token's output row): only for k <= 2, where bf16 accumulation is
+        // order-independent (0 + a exact, a + b commutative) and therefore bit-identical to the deterministic gather;
+        // k > 2 keeps the gather so results do not depend on arrival order
         const char* f = getenv("FM_FUSED_COMBINE");
-        ctx->fused = (f != nullptr && *f) ? atoi(f) != 0 : false;
+        ctx->fused = ((f != nullptr && *f) ? atoi(f) != 0 : true) && d.k <= 2;
         if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
     }
     ctx->tpc = ceil_div(d.S, ctx->grid);

@@ -260,19 +260,19 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                                 const int h = pg + i * 256 + lane * 8;
                                 if (h < hc_len) {
                                     const __nv_bfloat16* wrow = wg_s + (size_t)(g8 * 8) * Hc + h;
+                                    float xf[4][8];   // the 4 tokens' 8 columns, unpacked once per piece
+#pragma unroll
+                                    for (int tk = 0; tk < 4; ++tk) unpack8(xv[tk][i], xf[tk]);
 #pragma unroll
                                     for (int e = 0; e < 8; ++e) {
                                         if (e < ne) {
                                             float wf[8];
                                             unpack8(*reinterpret_cast<const uint4*>(wrow + (size_t)e * Hc), wf);
 #pragma unroll
-                                            for (int tk = 0; tk < 4; ++tk) {
-                                                float xf[8];
-                                                unpack8(xv[tk][i], xf);
+                                            for (int tk = 0; tk < 4; ++tk)
 #pragma unroll
                                                 for (int q = 0; q < 8; ++q)
-                                                    acc[tk * 8 + e] = fmaf(xf[q], wf[q], acc[tk * 8 + e]);
-                                            }
+                                                    acc[tk * 8 + e] = fmaf(xf[tk][q], wf[q], acc[tk * 8 + e]);
                                         }
                                     }
                                 }
@@ -386,55 +386,48 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     }
     __syncthreads();
     if (tid == 0) trace_stamp(p, 8);
-    for (int tp = warp * 2; tp < n_tok; tp += NUM_WARPS * 2) {   // two token rows in flight per warp
-        __nv_bfloat16* dst[2][8];
-        bool keep[2][8];
-        const int nt2 = min(2, n_tok - tp);
+    for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
+        const int t = t0 + ti;
+        __nv_bfloat16* dst[8];
+        bool keep[8];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int ti = tp + u, t = t0 + ti;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                keep[u][j] = false;
-                dst[u][j] = nullptr;
-                if (u < nt2 && j < k) {
-                    const int e = sel_e[ti * k + j];
-                    const int s = base_s[e] + rank_s[ti * k + j];
-                    if (lane == 0) p.slot[(size_t)t * k + j] = s;
-                    keep[u][j] = s < p.EC;
-                    const int owner = e / p.nLx, le = e - owner * p.nLx;
-                    if (p.fused && lane == 0 && keep[u][j]) {   // what the expert's GEMM1 epilogue needs to combine this row
-                        uint4 m;
-                        m.x = (unsigned int)t;
-                        m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
-                        m.z = __float_as_uint(p.mcw[t]);
-                        m.w = 0u;
-                        st_global_v4(p.peer_recv_meta[owner] + (size_t)(p.rank * p.nLx + le) * p.pEC + s, m);
-                    }
-                    dst[u][j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[u][j] ? s : 0)) * H;
+        for (int j = 0; j < 8; ++j) {
+            keep[j] = false;
+            dst[j] = nullptr;
+            if (j < k) {
+                const int e = sel_e[ti * k + j];
+                const int s = base_s[e] + rank_s[ti * k + j];
+                if (lane == 0) p.slot[(size_t)t * k + j] = s;
+                keep[j] = s < p.EC;
+                const int owner = e / p.nLx, le = e - owner * p.nLx;
+                if (p.fused && lane == 0 && keep[j]) {   // what the expert's GEMM1 epilogue needs to combine this row
+                    uint4 m;
+                    m.x = (unsigned int)t;
+                    m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
+                    m.z = __float_as_uint(p.mcw[t]);
+                    m.w = 0u;
+                    st_global_v4(p.peer_recv_meta[owner] + (size_t)(p.rank * p.nLx + le) * p.pEC + s, m);
                 }
+                dst[j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[j] ? s : 0)) * H;
             }
         }
+        const __nv_bfloat16* src = p.x + (size_t)t * H;
         for (int hg = 0; hg < H; hg += 1024) {
-            uint4 v[2][4];
+            uint4 v[4];
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int i = 0; i < 4; ++i) {
+                const int h = hg + i * 256 + lane * 8;
+                if (h < H) v[i] = ld_global_nc_v4(src + h);
+            }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int h = hg + i * 256 + lane * 8;
-                    if (u < nt2 && h < H) v[u][i] = ld_global_nc_v4(p.x + (size_t)(t0 + tp + u) * H + h);
+            for (int i = 0; i < 4; ++i) {
+                const int h = hg + i * 256 + lane * 8;
+                if (h < H) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < k && keep[j]) st_global_v4(dst[j] + h, v[i]);
                 }
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int h = hg + i * 256 + lane * 8;
-                    if (u < nt2 && h < H) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            if (j < k && keep[u][j]) st_global_v4(dst[u][j] + h, v[u][i]);
-                    }
-                }
+            }
         }
     }
     __syncthreads();
@@ -657,6 +650,7 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
     int stage = 0, phase = 0, q = 0, qphase = 0, as = 0, aphase = 0;
+    bool first_tile = true;
     for (;;) {
         int kind = -1, nk = 0, bn = BLOCK_N;
         if (lane == 0) {
@@ -676,6 +670,7 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
             const uint32_t d_tmem = tmem_base + (uint32_t)as * BLOCK_N;
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait(&full[stage], phase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, stage);
+                if (first_tile && (kb == 0 || kb == 4 || kb == nk - 1)) trace_stamp(p, kb == 0 ? 13 : (kb == 4 ? 14 : 15));
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * PC::STAGE_BYTES);
                 const uint64_t da = umma_smem_desc_sw128(sa);
@@ -696,6 +691,7 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
             if (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
+        first_tile = false;
         __syncwarp();
     }
 }

@@ -115,7 +115,7 @@ def stage(args):
         ctx.forward(xd, wgd, wed, out=out); ctx.synchronize()
         tr = ctx.read("trace").astype(np.int64)
         t00 = tr[:, 0].min()
-        names = ["start", "gate", "barrier", "dispatch", "ffn_start", "ffn_end", "combine_end", "", "disp_base", "disp_rows", "", "gate_gemv", "gate_softmax"]
+        names = ["start", "gate", "barrier", "dispatch", "ffn_start", "ffn_end", "combine_end", "", "disp_base", "disp_rows", "", "gate_gemv", "gate_softmax", "t0_kb0_full", "t0_kb4_full", "t0_last_full"]
         for i, nm in enumerate(names):
             if not nm: continue
             v = (tr[:, i] - t00) / 1e3
