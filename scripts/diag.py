@@ -154,6 +154,12 @@ def stage(args):
         k0 = [ (done[c,i]-max(done[c,i-1] if i>0 else tr[c,4], ready[c,i]))/1e3 for c in range(tr.shape[0]) for i in range(int(ntiles[c]))]
         k0 = np.array(k0); short = k0[k0 < 15]; long_ = k0[k0 >= 15]
         if len(short) and len(long_): print(f"  short tiles n={len(short)} mean {short.mean():.2f} us; long tiles n={len(long_)} mean {long_.mean():.2f} us")
+        ep = tr[:, 120:125]
+        if (ep[:, 0] > 0).any():
+            m = ep[:, 0] > 0
+            d = (ep[m, 1:] - ep[m, :1]) / 1e3
+            print("  epilogue of tile #2 (us after tmem_full): chunk0 %.2f drain_all %.2f barrier %.2f published %.2f" % tuple(np.median(d, axis=0)))
+            print("  tile #2: ready->tmem_full %.2f us (med)" % np.median((ep[m, 0] - ready[m, 2]) / 1e3))
         np.save("gpurun_out/trace_%s.npy" % args.cfg, tr)
     ctx.close()
 
