@@ -705,6 +705,91 @@ __device__ __noinline__ float gelu_erf(float v) {   // GELU, erf form (cutlass::
     return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));
 }
 
+enum : int { EPI_G0_RELU = 0, EPI_G0_GELU = 1, EPI_G1_STORE = 2, EPI_G1_FUSED_ADD = 3, EPI_G1_FUSED_COPY = 4 };
+
+struct DrainArgs {
+    uint8_t* stg;                  // this warp's 32 x 144 B transpose tile
+    uint32_t t_row;                // TMEM address of this warp's lane quarter, accumulator column 0
+    int nchunks, lane, quarter, my_rows, N, n0;
+    const __nv_bfloat16* bias;     // [N] or nullptr
+    __nv_bfloat16* out_rows;       // row 0 of the destination row block (h staging or return buffer)
+    __nv_bfloat16* acc_base;       // fused GEMM1: the source rank's output accumulator
+    int my_tok;                    // fused GEMM1: token of accumulator row (quarter*32 + lane)
+    float my_pw, my_mcw;
+    uint64_t* release_bar;         // tmem_empty barrier of this accumulator
+    uint32_t crank;
+    bool stamp;
+};
+
+// TMEM -> registers (thread = accumulator row) -> bias / activation / combine scaling in fp32 -> bf16 (RNE) -> smem
+// transpose -> full-line 16-byte global stores (or REDG adds).  64 accumulator columns per step.
+template <int MODE, bool HAS_BIAS, bool PAIR>
+__device__ __forceinline__ void drain_accumulator(const FmParams& p, const DrainArgs& a) {
+    uint8_t* my_row = a.stg + a.lane * EPI_ROW_BYTES;
+    for (int c = 0; c < a.nchunks; ++c) {
+        uint32_t v[2][32];
+        tmem_ld_32x32b_x32(a.t_row + c * 64, v[0]);
+        tmem_ld_32x32b_x32(a.t_row + c * 64 + 32, v[1]);
+        tmem_ld_wait();
+        if (c == a.nchunks - 1) {  // last TMEM read of this accumulator: hand it back to the MMA issuer
+            tcgen05_fence_before();
+            __syncwarp();
+            if (a.lane == 0) release_to_leader<PAIR>(a.release_bar, a.crank);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {   // 8 columns -> one 16-byte smem store
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[half][g * 8 + i]);
+                if (HAS_BIAS) {
+                    float bv[8];
+                    unpack8(ld_global_nc_v4(a.bias + a.n0 + c * 64 + half * 32 + g * 8), bv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] += bv[i];
+                }
+                if (MODE == EPI_G0_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);                 // ReLU (types.cuh:151-159)
+                } else if (MODE == EPI_G0_GELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+                } else if (MODE == EPI_G1_FUSED_ADD) {
+                    // the reference's combine arithmetic on the bf16-rounded y (processor.cuh:110-169):
+                    // term = rne( p~ (x) rne( y / mCw ) ); the bf16 accumulation itself is the REDG below
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) f[i] = a.my_pw * rne_bf16(__fdividef(rne_bf16(f[i]), a.my_mcw));
+                }
+                uint4 o;
+                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(my_row + (half * 4 + g) * 16) = o;
+            }
+        }
+        __syncwarp();
+        // transposed read-back: 8 lanes cover one row's 128 bytes, 4 rows per instruction, full-line stores
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (a.lane >> 3), seg = a.lane & 7;
+            const uint4 o = *reinterpret_cast<const uint4*>(a.stg + r * EPI_ROW_BYTES + seg * 16);
+            const int row_in_tile = a.quarter * 32 + r;
+            if (MODE == EPI_G1_FUSED_ADD || MODE == EPI_G1_FUSED_COPY) {
+                // row -> its token's output row on the source rank (k == 1: plain copy, reference processor.cuh:170-203)
+                const int tok = __shfl_sync(0xffffffffu, a.my_tok, r);
+                if (row_in_tile < a.my_rows) {
+                    __nv_bfloat16* dst = a.acc_base + (size_t)tok * a.N + a.n0 + c * 64 + seg * 8;
+                    if (MODE == EPI_G1_FUSED_ADD) red_add_bf16x8(dst, o); else st_global_v4(dst, o);
+                }
+            } else if (row_in_tile < a.my_rows) {
+                st_global_v4(a.out_rows + (size_t)row_in_tile * a.N + a.n0 + c * 64 + seg * 8, o);
+            }
+        }
+        __syncwarp();
+        if (a.stamp && c == 0) trace_stamp(p, 121);
+    }
+}
+
 // warps 4-7 of every CTA: TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced global / peer stores
 template <bool PAIR>
 __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base,
@@ -741,7 +826,6 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)my_mblk * BLOCK_M) * p.H;
         }
         const int nchunks = my_rows > 0 ? min(ti.bn / 64, (N - n0) / 64) : 0;
-        const bool relu = p.act == 0;
         // fused GEMM1 -> combine: this thread owns accumulator row (quarter*32 + lane); fetch that row's routing record
         const bool fuse = p.fused != 0 && ti.kind == 1;
         int my_tok = 0;
@@ -759,71 +843,32 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         const bool stamp_tile = (ntiles == 2) && tid == EPI_WARP0 * 32;
         if (stamp_tile) trace_stamp(p, 120);
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * BLOCK_N;
-        for (int c = 0; c < nchunks; ++c) {
-            uint32_t v0[32], v1[32];
-            tmem_ld_32x32b_x32(t_row + c * 64, v0);
-            tmem_ld_32x32b_x32(t_row + c * 64 + 32, v1);
-            tmem_ld_wait();
-            if (c == nchunks - 1) {  // last TMEM read of this accumulator: hand it back to the MMA issuer
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) release_to_leader<PAIR>(&tmem_empty[as], crank);
-            }
-            float bv[8];
-            uint8_t* my_row = stg + lane * EPI_ROW_BYTES;
-#pragma unroll
-            for (int g8 = 0; g8 < 8; ++g8) {   // 8 groups of 8 columns -> one 16-byte smem store each
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int col = g8 * 8 + i;
-                    f[i] = __uint_as_float(col < 32 ? v0[col] : v1[col - 32]);
+        {
+            DrainArgs da;
+            da.stg = stg; da.t_row = t_row; da.nchunks = nchunks; da.lane = lane; da.quarter = quarter;
+            da.my_rows = my_rows; da.N = N; da.n0 = n0; da.bias = bias; da.out_rows = out_rows; da.acc_base = acc_base;
+            da.my_tok = my_tok; da.my_pw = my_pw; da.my_mcw = my_mcw; da.release_bar = &tmem_empty[as]; da.crank = crank;
+            da.stamp = stamp_tile;
+            // one specialised instantiation per (epilogue kind, bias) pair: no per-element or per-group branching
+            const int mode = ti.kind == 0 ? (p.act == 0 ? EPI_G0_RELU : EPI_G0_GELU)
+                                          : (!fuse ? EPI_G1_STORE : (p.k > 1 ? EPI_G1_FUSED_ADD : EPI_G1_FUSED_COPY));
+            if (bias == nullptr) {
+                switch (mode) {
+                    case EPI_G0_RELU: drain_accumulator<EPI_G0_RELU, false, PAIR>(p, da); break;
+                    case EPI_G0_GELU: drain_accumulator<EPI_G0_GELU, false, PAIR>(p, da); break;
+                    case EPI_G1_STORE: drain_accumulator<EPI_G1_STORE, false, PAIR>(p, da); break;
+                    case EPI_G1_FUSED_ADD: drain_accumulator<EPI_G1_FUSED_ADD, false, PAIR>(p, da); break;
+                    default: drain_accumulator<EPI_G1_FUSED_COPY, false, PAIR>(p, da); break;
                 }
-                if (bias != nullptr) {
-                    unpack8(ld_global_nc_v4(bias + n0 + c * 64 + g8 * 8), bv);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] += bv[i];
-                }
-                if (ti.kind == 0) {
-                    // branch on the activation OUTSIDE the element loop: a per-element select makes the compiler
-                    // evaluate erff for every element even for ReLU (measured: 7.3 us instead of ~2 us per tile)
-                    if (relu) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);          // ReLU (types.cuh:151-159)
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
-                    }
-                } else if (fuse && p.k > 1) {
-                    // the reference's combine arithmetic on the bf16-rounded y (processor.cuh:110-169):
-                    // term = rne( p~ (x) rne( y / mCw ) ); the bf16 accumulation itself is the REDG below
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) f[i] = my_pw * rne_bf16(__fdividef(rne_bf16(f[i]), my_mcw));
-                }
-                uint4 o;
-                o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(my_row + g8 * 16) = o;
-            }
-            __syncwarp();
-            // transposed read-back: 8 lanes cover one row's 128 bytes, 4 rows per instruction, full-line stores
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + (lane >> 3), seg = lane & 7;
-                const uint4 o = *reinterpret_cast<const uint4*>(stg + r * EPI_ROW_BYTES + seg * 16);
-                const int row_in_tile = quarter * 32 + r;
-                if (fuse) {   // row -> its token's output row on the source rank (k == 1: plain copy, reference :170-203)
-                    const int tok = __shfl_sync(0xffffffffu, my_tok, r);
-                    if (row_in_tile < my_rows) {
-                        __nv_bfloat16* dst = acc_base + (size_t)tok * N + n0 + c * 64 + seg * 8;
-                        if (p.k > 1) red_add_bf16x8(dst, o); else st_global_v4(dst, o);
-                    }
-                } else if (row_in_tile < my_rows) {
-                    st_global_v4(out_rows + (size_t)row_in_tile * N + n0 + c * 64 + seg * 8, o);
+            } else {
+                switch (mode) {
+                    case EPI_G0_RELU: drain_accumulator<EPI_G0_RELU, true, PAIR>(p, da); break;
+                    case EPI_G0_GELU: drain_accumulator<EPI_G0_GELU, true, PAIR>(p, da); break;
+                    case EPI_G1_STORE: drain_accumulator<EPI_G1_STORE, true, PAIR>(p, da); break;
+                    case EPI_G1_FUSED_ADD: drain_accumulator<EPI_G1_FUSED_ADD, true, PAIR>(p, da); break;
+                    default: drain_accumulator<EPI_G1_FUSED_COPY, true, PAIR>(p, da); break;
                 }
             }
-            __syncwarp();
-            if (stamp_tile && c == 0) trace_stamp(p, 121);
         }
         if (stamp_tile) trace_stamp(p, 122);
         if (nchunks <= 0) {  // nothing to drain (row block past the packet's rows): still release the accumulator
