@@ -104,6 +104,7 @@ struct fm_ctx {
     int TN0 = 0, TN1 = 0, num_pkts = 0, num_blocks = 0, total_items = 0;
     int bn0 = 256, bn1 = 256, claim_ahead_kb = 8;
     int dbg_flags = 0;
+    int prefetch_kb = 0;
     bool pair = false;   // cta_group::2: two CTAs (one cluster) per 256-row tile
     uint32_t epoch = 0;
     unsigned long long bar_count = 0;
@@ -263,7 +264,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.EC = d.EC; p.pEC = d.pEC; p.TCM = d.TCM; p.act = c->cfg.hidden_act;
     p.TN0 = c->TN0; p.TN1 = c->TN1; p.tpc = c->tpc; p.num_pkts = c->num_pkts; p.num_blocks = c->num_blocks;
     p.total_items = c->total_items;
-    p.bn[0] = c->bn0; p.bn[1] = c->bn1; p.claim_ahead_kb = c->claim_ahead_kb; p.dbg_flags = c->dbg_flags;
+    p.bn[0] = c->bn0; p.bn[1] = c->bn1; p.claim_ahead_kb = c->claim_ahead_kb; p.dbg_flags = c->dbg_flags; p.prefetch_kb = c->prefetch_kb;
     if (phase_mask & 1u) {
         c->epoch += 1;
         c->bar_count += (unsigned long long)c->grid;
@@ -420,6 +421,8 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->bn1 = env_int("FM_BN1", 256) == 128 ? 128 : 256;
     ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 8);
     ctx->dbg_flags = env_int("FM_DBG_FLAGS", 0);
+    ctx->prefetch_kb = env_int("FM_PREFETCH_KB", 0);
+    if (ctx->prefetch_kb < 0) ctx->prefetch_kb = 0;
     if (ctx->claim_ahead_kb < 0) ctx->claim_ahead_kb = 0;
     ctx->TN0 = ceil_div(d.P, ctx->bn0);
     ctx->TN1 = ceil_div(d.H, ctx->bn1);

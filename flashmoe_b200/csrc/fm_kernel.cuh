@@ -89,6 +89,7 @@ struct FmParams {
     int TN0, TN1, tpc, num_pkts, num_blocks, total_items;
     int bn[2];          // tile width of GEMM0 / GEMM1 (128 or 256)
     int claim_ahead_kb; // the scheduler claims the next tile when this many k-blocks of the current one remain
+    int prefetch_kb;    // L2 prefetch distance of the TMA producer in k-blocks (0 = off)
     int dbg_flags;      // experiments only: bit0 = skip TMA loads, bit1 = skip MMA issue (results are garbage)
     unsigned int epoch, phase_mask;
     unsigned long long bar_target, timeout_ns;
@@ -490,7 +491,7 @@ __device__ __forceinline__ void wait_sched_full(const FmParams& p, uint64_t* bar
 // consumers of a ring slot release it on the LEADER's barrier (the scheduler lives there)
 template <bool PAIR>
 __device__ __forceinline__ void release_to_leader(uint64_t* bar, uint32_t crank) {
-    if (PAIR && crank != 0) mbar_arrive_cluster(bar, 0);
+    if (PAIR && crank != 0) mbar_arrive_cluster_plain(bar, 0);
     else mbar_arrive(bar);
 }
 
@@ -615,16 +616,27 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
             const int a_row = ti.a_row + (PAIR ? (int)crank * BLOCK_M : 0);
             const int b_row = ti.b_row + (PAIR ? (int)crank * b_rows : 0);
             const int take_at = min(ti.nk - 1, max(0, ti.nk - p.claim_ahead_kb));
+            const int pf = p.prefetch_kb;
+            if (pf > 0) {   // warm L2 for the k-blocks just beyond the smem pipeline
+                for (int kb = PC::STAGES; kb < min(ti.nk, PC::STAGES + pf); ++kb) {
+                    tma_prefetch_l2_2d(ta, kb * BLOCK_K, a_row);
+                    tma_prefetch_l2_2d(tb, kb * BLOCK_K, b_row);
+                }
+            }
             for (int kb = 0; kb < ti.nk; ++kb) {
+                if (pf > 0 && kb + PC::STAGES + pf < ti.nk) {
+                    tma_prefetch_l2_2d(ta, (kb + PC::STAGES + pf) * BLOCK_K, a_row);
+                    tma_prefetch_l2_2d(tb, (kb + PC::STAGES + pf) * BLOCK_K, b_row);
+                }
                 if (kb == take_at && crank == 0) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
                 uint8_t* sa = smem + stage * PC::STAGE_BYTES;
                 if (p.dbg_flags & 1) {   // experiment: no loads, barrier traffic only
-                    if (PAIR && crank != 0) mbar_arrive_cluster(&full[stage], 0);
+                    if (PAIR && crank != 0) mbar_arrive_cluster_plain(&full[stage], 0);
                     else mbar_arrive(&full[stage]);
                 } else if (PAIR) {
                     if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * tx_cta);
-                    else mbar_arrive_cluster(&full[stage], 0);
+                    else mbar_arrive_cluster_plain(&full[stage], 0);
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[stage]), 0);
                     tma_load_2d_pair(sa, ta, kb * BLOCK_K, a_row, leader_full);
                     tma_load_2d_pair(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, leader_full);

@@ -191,6 +191,12 @@ __device__ __forceinline__ void red_add_bf16x8(void* p, const uint4& v) {
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
+// L2 prefetch of a tensor tile (no smem destination, no barrier): hides HBM latency for k-blocks the pipeline will
+// request a few steps later
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int32_t c0, int32_t c1,
                                             uint64_t* bar) {
     asm volatile(
@@ -270,6 +276,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {  // arrive on CTA `cta`'s copy
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_shared(smem_u32(bar), cta))
                  : "memory");
+}
+// barrier-only signal to another CTA (no data published by this thread): default semantics, no cluster-scope release
+// fence (a .release.cluster arrive per k-block made the CTA-pair pipeline ~2x slower)
+__device__ __forceinline__ void mbar_arrive_cluster_plain(uint64_t* bar, uint32_t cta) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(mapa_shared(smem_u32(bar), cta)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {  // acquire at cluster scope
     uint32_t ok;
