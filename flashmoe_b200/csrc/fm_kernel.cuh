@@ -48,8 +48,9 @@ constexpr int OFF_BARS = OFF_EPI + 4 * EPI_WARP_BYTES;                // 215040
 constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_TMEM_FULL = 2 * MAX_STAGES, BAR_TMEM_EMPTY = BAR_TMEM_FULL + 2;
 constexpr int BAR_SCHED_FULL = BAR_TMEM_EMPTY + 2, BAR_SCHED_EMPTY = BAR_SCHED_FULL + NSCHED;
 constexpr int BAR_PROD_TAKE = BAR_SCHED_EMPTY + NSCHED;
-constexpr int NUM_BARS = BAR_PROD_TAKE + NSCHED;                      // 28
-constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 215264 (16-byte aligned)
+constexpr int BAR_XROWS = BAR_PROD_TAKE + NSCHED;                     // dispatch phase: bulk row load
+constexpr int NUM_BARS = BAR_XROWS + 1;                               // 29 (+1 pad to keep the ring 16-byte aligned)
+constexpr int OFF_RING = OFF_BARS + (NUM_BARS + 1) * 8;               // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
 constexpr int SMEM_USED = OFF_MISC + 64;
@@ -71,6 +72,7 @@ constexpr int G_LOGIT_BYTES = 65536;
 constexpr int G_OFF_SEL = 131072;        // int16 sel_e[tpc*k] then int32 rank[tpc*k]   <= 48 KiB
 constexpr int G_SEL_MAX = 8192;          // max tpc*k
 constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E]        <= 4 KiB (E <= 1024)
+constexpr int G_XROWS_BYTES = 131072;       // dispatch: staged token rows (reuses the Wg / logits scratch)
 static_assert(G_OFF_BASE + 4096 <= OFF_EPI, "gate scratch must fit in the stage area");
 
 struct TileBlock {  // one contiguous run of work items: all tiles of one GEMM of one packet
@@ -388,50 +390,55 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     }
     __syncthreads();
     if (tid == 0) trace_stamp(p, 8);
-    for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
-        const int t = t0 + ti;
-        __nv_bfloat16* dst[8];
-        bool keep[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            keep[j] = false;
-            dst[j] = nullptr;
-            if (j < k) {
-                const int e = sel_e[ti * k + j];
-                const int s = base_s[e] + rank_s[ti * k + j];
-                if (lane == 0) p.slot[(size_t)t * k + j] = s;
-                keep[j] = s < p.EC;
+    // Row copies through the TMA engine: the chunk's token rows are contiguous in x, so one bulk load stages up to
+    // 128 KiB of them in shared memory and every kept (token, pick) pair is one bulk store of a whole row into the
+    // owner rank's receive buffer (peer-mapped over NVLink).  No per-lane load/store latency chains.
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;
+    uint8_t* x_s = smem;   // the router's Wg / logits scratch is free now
+    if (tid == 0) {
+        mbar_init(xbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int row_bytes = H * 2;
+    const int rows_per_group = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
+    uint32_t xphase = 0;
+    for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
+        const int rows = min(rows_per_group, n_tok - g0);
+        if (tid == 0) {
+            mbar_arrive_expect_tx(xbar, (uint32_t)(rows * row_bytes));
+            bulk_load_1d(x_s, p.x + (size_t)(t0 + g0) * H, (uint32_t)(rows * row_bytes), xbar);
+        }
+        mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 900);
+        xphase ^= 1;
+        for (int i = tid; i < rows * k; i += NUM_THREADS) {
+            const int tl = i / k, j = i - tl * k;
+            const int ti = g0 + tl, t = t0 + ti;
+            const int e = sel_e[ti * k + j];
+            const int s = base_s[e] + rank_s[ti * k + j];
+            p.slot[(size_t)t * k + j] = s;
+            if (s < p.EC) {
                 const int owner = e / p.nLx, le = e - owner * p.nLx;
-                if (p.fused && lane == 0 && keep[j]) {   // what the expert's GEMM1 epilogue needs to combine this row
+                const size_t row = (size_t)(p.rank * p.nLx + le) * p.pEC + s;
+                if (p.fused) {   // what the expert's GEMM1 epilogue needs to combine this row
                     uint4 m;
                     m.x = (unsigned int)t;
                     m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
                     m.z = __float_as_uint(p.mcw[t]);
                     m.w = 0u;
-                    st_global_v4(p.peer_recv_meta[owner] + (size_t)(p.rank * p.nLx + le) * p.pEC + s, m);
+                    st_global_v4(p.peer_recv_meta[owner] + row, m);
                 }
-                dst[j] = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + le) * p.pEC + (keep[j] ? s : 0)) * H;
+                bulk_store_1d(p.peer_recv_x[owner] + row * H, x_s + (size_t)tl * row_bytes, (uint32_t)row_bytes);
             }
         }
-        const __nv_bfloat16* src = p.x + (size_t)t * H;
-        for (int hg = 0; hg < H; hg += 1024) {
-            uint4 v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = hg + i * 256 + lane * 8;
-                if (h < H) v[i] = ld_global_nc_v4(src + h);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = hg + i * 256 + lane * 8;
-                if (h < H) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j < k && keep[j]) st_global_v4(dst[j] + h, v[i]);
-                }
-            }
+        bulk_commit_group();
+        if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the stores have read it
+            bulk_wait_group_read0();
+            __syncthreads();
         }
     }
+    bulk_wait_group0();        // this thread's row stores are complete ...
+    fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy flag traffic below
     __syncthreads();
     if (tid == 0) trace_stamp(p, 9);
     if (tid == 0) {
