@@ -71,9 +71,9 @@ constexpr int G_OFF_LOGIT = 65536;       // f32  [TS][E+1]          <= 64 KiB
 constexpr int G_LOGIT_BYTES = 65536;
 constexpr int G_OFF_SEL = 131072;        // int16 sel_e[tpc*k] then int32 rank[tpc*k]   <= 48 KiB
 constexpr int G_SEL_MAX = 8192;          // max tpc*k
-constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E]        <= 4 KiB (E <= 1024)
+constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E] + total[E]   <= 8 KiB (E <= 1024)
 constexpr int G_XROWS_BYTES = 131072;       // dispatch: staged token rows (reuses the Wg / logits scratch)
-static_assert(G_OFF_BASE + 4096 <= OFF_EPI, "gate scratch must fit in the stage area");
+static_assert(G_OFF_BASE + 8192 <= OFF_EPI, "gate scratch must fit in the stage area");
 
 struct TileBlock {  // one contiguous run of work items: all tiles of one GEMM of one packet
     int kind;       // 0 = GEMM0 (x.W_up^T), 1 = GEMM1 (h.W_down^T)
@@ -335,13 +335,6 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         __syncthreads();
     }
     if (tid == 0) trace_stamp(p, 12);
-    if (p.fused) {   // accumulation target rows start at zero (reference clearState zeroes the output, moe.cuh:43-48)
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
-            __nv_bfloat16* row = p.out_acc + (size_t)(t0 + ti) * H;
-            for (int h = lane * 8; h < H; h += 256) st_global_v4(row + h, z);
-        }
-    }
     // position of every (token, pick) among this chunk's selections of the same expert, ascending token order:
     // one thread per entry counts the equal selections before it (warp-broadcast smem reads); totals by smem atomics
     int* cnt_s = reinterpret_cast<int*>(smem + G_OFF_BASE);
@@ -366,40 +359,44 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
 // The last CTA to finish publishes one 8-byte flag {epoch, rows} per expert (os/packet.cuh:214-237; a flag is
 // also sent for 0 rows, like the reference's "noop" signal).
 // ============================================================================================================
+constexpr int DISP_THREADS = 160;   // warps 2,4,5,6,7; warps 0,1,3 are already in their FFN roles (producer / MMA / scheduler)
+__device__ __forceinline__ void disp_sync() { asm volatile("bar.sync 2, 160;" ::: "memory"); }
+
 __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tid = (warp == 2 ? 0 : (warp - 3) * 32) + lane;   // 0..159 within the dispatch subset
     const int E = p.E, H = p.H, k = p.k, G = gridDim.x;
     const int16_t* sel_e = reinterpret_cast<const int16_t*>(smem + G_OFF_SEL);
     const int* rank_s = reinterpret_cast<const int*>(smem + G_OFF_SEL + G_SEL_MAX * 2);
-    int* base_s = reinterpret_cast<int*>(smem + G_OFF_BASE);
+    int* base_s = reinterpret_cast<int*>(smem + G_OFF_BASE);        // selections of e by lower chunks
+    int* total_s = base_s + 1024;                                    // selections of e by all chunks
     unsigned int* misc = reinterpret_cast<unsigned int*>(smem + OFF_MISC);
 
-    // base[e] = selections of e by lower chunks: all 256 threads sum the [blockIdx.x, E] prefix of chunk_counts
-    for (int e = tid; e < E; e += NUM_THREADS) base_s[e] = 0;
-    __syncthreads();
+    // one pass over chunk_counts [G, E] gives both the prefix (lower chunks) and the totals every CTA may have to publish
+    for (int e = tid; e < E; e += DISP_THREADS) { base_s[e] = 0; total_s[e] = 0; }
+    disp_sync();
     {
-        const int n = (int)blockIdx.x * E;
-        int part = 0, cur_e = -1;
-        for (int i = tid; i < n; i += NUM_THREADS) {
+        const int nb = (int)blockIdx.x * E, n = G * E;
+        const bool fixed_e = (E <= DISP_THREADS) && (DISP_THREADS % E) == 0;   // then a thread always meets one e
+        int part_b = 0, part_t = 0, cur_e = -1;
+        for (int i = tid; i < n; i += DISP_THREADS) {
             const int e = i % E;
             const int v = p.chunk_counts[i];
-            if (E <= NUM_THREADS && (NUM_THREADS % E) == 0) { part += v; cur_e = e; }   // a thread always sees one e
-            else atomicAdd(&base_s[e], v);
+            if (fixed_e) { part_t += v; if (i < nb) part_b += v; cur_e = e; }
+            else if (v != 0) { atomicAdd(&total_s[e], v); if (i < nb) atomicAdd(&base_s[e], v); }
         }
-        if (cur_e >= 0 && part != 0) atomicAdd(&base_s[cur_e], part);
+        if (cur_e >= 0) {
+            if (part_t != 0) atomicAdd(&total_s[cur_e], part_t);
+            if (part_b != 0) atomicAdd(&base_s[cur_e], part_b);
+        }
     }
-    __syncthreads();
+    disp_sync();
     if (tid == 0) trace_stamp(p, 8);
     // Row copies through the TMA engine: the chunk's token rows are contiguous in x, so one bulk load stages up to
     // 128 KiB of them in shared memory and every kept (token, pick) pair is one bulk store of a whole row into the
     // owner rank's receive buffer (peer-mapped over NVLink).  No per-lane load/store latency chains.
-    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;
+    uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;   // initialised in the kernel prologue
     uint8_t* x_s = smem;   // the router's Wg / logits scratch is free now
-    if (tid == 0) {
-        mbar_init(xbar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
     const int row_bytes = H * 2;
     const int rows_per_group = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
     uint32_t xphase = 0;
@@ -409,9 +406,15 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             mbar_arrive_expect_tx(xbar, (uint32_t)(rows * row_bytes));
             bulk_load_1d(x_s, p.x + (size_t)(t0 + g0) * H, (uint32_t)(rows * row_bytes), xbar);
         }
+        if (g0 == 0 && p.fused) {   // while the rows are in flight: the accumulation target rows start at zero
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);   // (reference clearState zeroes the output, moe.cuh:43-48)
+            const int vec_per_row = H >> 3;
+            for (int i = tid; i < n_tok * vec_per_row; i += DISP_THREADS)
+                st_global_v4(p.out_acc + (size_t)t0 * H + (size_t)i * 8, z);
+        }
         mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 900);
         xphase ^= 1;
-        for (int i = tid; i < rows * k; i += NUM_THREADS) {
+        for (int i = tid; i < rows * k; i += DISP_THREADS) {
             const int tl = i / k, j = i - tl * k;
             const int ti = g0 + tl, t = t0 + ti;
             const int e = sel_e[ti * k + j];
@@ -434,12 +437,12 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         bulk_commit_group();
         if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the stores have read it
             bulk_wait_group_read0();
-            __syncthreads();
+            disp_sync();
         }
     }
     bulk_wait_group0();        // this thread's row stores are complete ...
     fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy flag traffic below
-    __syncthreads();
+    disp_sync();
     if (tid == 0) trace_stamp(p, 9);
     if (tid == 0) {
         fence_acq_rel_sys();  // this CTA's row stores (observed through the barrier) before the counter bump
@@ -447,17 +450,19 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         misc[0] = (old == (unsigned int)G - 1u) ? 1u : 0u;
         if (misc[0]) fence_acq_rel_sys();
     }
-    __syncthreads();
-    if (misc[0]) {  // last CTA: every chunk's rows are out; publish counts to the owners
-        for (int e = tid; e < E; e += NUM_THREADS) base_s[e] = 0;
-        __syncthreads();
-        for (int i = tid; i < G * E; i += NUM_THREADS) {
-            const int v = p.chunk_counts[i];
-            if (v != 0) atomicAdd(&base_s[i % E], v);
-        }
-        __syncthreads();
-        for (int e = tid; e < E; e += NUM_THREADS) {
-            const int tot = base_s[e];
+    disp_sync();
+    // the totals live in the pipeline stage area, which this CTA's own TMA producer may start filling as soon as the
+    // first flag below is visible: read them into registers first (E <= 1024 => at most 7 per thread)
+    int tot_r[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) tot_r[i] = (tid + i * DISP_THREADS < E) ? total_s[tid + i * DISP_THREADS] : 0;
+    disp_sync();
+    if (misc[0]) {  // last CTA to finish: every chunk's rows are out; publish {epoch, rows} to the owners
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const int e = tid + i * DISP_THREADS;
+            if (e >= E) break;
+            const int tot = tot_r[i];
             p.counts[e] = tot;
             const int rows = tot < p.EC ? tot : p.EC;
             const int owner = e / p.nLx, le = e - owner * p.nLx;
@@ -933,12 +938,12 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
     }
 }
 
+// kernel prologue: barriers of every later phase + TMEM; runs before the router so it costs nothing on the critical path
 template <bool PAIR>
-__device__ __forceinline__ void ffn_phase(const FmParams& p, uint8_t* smem) {
+__device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
     const int tid = threadIdx.x, warp = tid >> 5;
-    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
     if (warp == 1 && (tid & 31) == 0) {
         // arrival counts: full = leader's expect_tx (+ the peer producer's arrive); empty / tmem_full = one tcgen05.commit;
         // tmem_empty = one lane per epilogue warp (of both CTAs); sched_empty = producer(s) + MMA lane + epilogue warps
@@ -950,28 +955,38 @@ __device__ __forceinline__ void ffn_phase(const FmParams& p, uint8_t* smem) {
             mbar_init(&bars[BAR_SCHED_EMPTY + i], 1 + 5 * nc);
             mbar_init(&bars[BAR_PROD_TAKE + i], 1);
         }
+        mbar_init(&bars[BAR_XROWS], 1);
         fence_mbar_init();
     }
     if (warp == 0 && (tid & 31) == 0) {
         tma_prefetch_desc(&p.tm_a0); tma_prefetch_desc(&p.tm_b0);
         tma_prefetch_desc(&p.tm_a1); tma_prefetch_desc(&p.tm_b1);
     }
-    if (warp == 2) { if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
+    if (warp == 2 && (p.phase_mask & 2u)) { if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
     tcgen05_fence_before();
-    if (PAIR) cluster_sync_all(); else __syncthreads();   // barriers of BOTH CTAs initialised before any remote arrive
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
+}
 
-    if (tid == 0) trace_stamp(p, 4);
+// warp roles of the expert-FFN phase (entered per warp as soon as that warp is free; no block-wide sync on entry)
+template <bool PAIR>
+__device__ __forceinline__ void ffn_roles(const FmParams& p, uint8_t* smem, uint32_t crank) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
     if (warp == 0) ffn_producer<PAIR>(p, smem, bars, crank);
     else if (warp == 1) { if (crank == 0) ffn_mma<PAIR>(p, smem, bars, tmem_base); }
     else if (warp == 3) { if (crank == 0) ffn_scheduler<PAIR>(p, smem, bars); }
     else if (warp >= EPI_WARP0) ffn_epilogue<PAIR>(p, smem, bars, tmem_base, crank);
+}
 
+template <bool PAIR>
+__device__ __forceinline__ void ffn_teardown(const FmParams& p, uint8_t* smem) {
+    const int tid = threadIdx.x, warp = tid >> 5;
     tcgen05_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();   // nobody leaves while the partner may still touch its smem/TMEM
     if (warp == 2) {
         tcgen05_fence_after();
+        const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
         if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
     }
     if (tid == 0) trace_stamp(p, 5);
@@ -1125,12 +1140,15 @@ template <bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __grid_constant__ FmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int t0 = blockIdx.x * p.tpc;
     const int n_tok = max(0, min(p.tpc, p.S - t0));
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
 
-    // per-launch reset of the work counters (reference clearState, moe.cuh:21-70); consumed only after the grid barrier
+    if (tid == 0) trace_stamp(p, 0);
+    ffn_setup<PAIR>(p, smem);   // mbarriers + TMEM for the later phases (visible to everyone after the next block sync)
     if (p.phase_mask & 1u) {
+        // per-launch reset of the work counters (reference clearState, moe.cuh:21-70); consumed only after the grid barrier
         if (blockIdx.x == 0) {
             for (int i = tid; i < p.num_pkts * p.TCM; i += NUM_THREADS) {
                 p.g0_done[i] = 0u;
@@ -1142,19 +1160,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
                 *p.disp_done = 0u;
             }
         }
-        if (tid == 0) trace_stamp(p, 0);
         gate_phase(p, smem, t0, n_tok);
         if (tid == 0) trace_stamp(p, 1);
-        grid_barrier(p);
+        grid_barrier(p);   // also a cluster-wide sync: the partner CTA's barriers are initialised before any remote arrive
         if (tid == 0) trace_stamp(p, 2);
-        dispatch_phase(p, smem, t0, n_tok);
-        if (tid == 0) trace_stamp(p, 3);
-    } else if (blockIdx.x == 0 && tid == 0) {
-        *p.claim = 0u;   // debug re-run of later phases on the previous routing
+    } else {
+        if (blockIdx.x == 0 && tid == 0) *p.claim = 0u;   // debug re-run of later phases on the previous routing
+        if (PAIR) cluster_sync_all(); else __syncthreads();
     }
-    __syncthreads();
 
-    if (p.phase_mask & 2u) ffn_phase<PAIR>(p, smem);
+    // From here the warps specialise.  Warps 0, 1, 3 (TMA producer, MMA issuer, tile scheduler) enter their FFN roles at
+    // once -- the scheduler claims its first tile and spins on the packet flag while warps 2, 4-7 dispatch this CTA's rows;
+    // warps 4-7 then become the epilogue.
+    const bool disp_warp = (warp == 2) || (warp >= EPI_WARP0);
+    if ((p.phase_mask & 1u) && disp_warp) {
+        dispatch_phase(p, smem, t0, n_tok);
+        if (warp == 2 && (tid & 31) == 0) trace_stamp(p, 3);
+    }
+    if (p.phase_mask & 2u) {
+        if (tid == EPI_WARP0 * 32) trace_stamp(p, 4);
+        ffn_roles<PAIR>(p, smem, crank);
+        ffn_teardown<PAIR>(p, smem);
+    }
 
     if (p.phase_mask & 4u) {
         __syncthreads();
