@@ -104,6 +104,7 @@ struct fm_ctx {
     int TN0 = 0, TN1 = 0, num_pkts = 0, num_blocks = 0, total_items = 0;
     int bn0 = 256, bn1 = 256, claim_ahead_kb = 8;
     int dbg_flags = 0;
+    bool coop = true;    // cooperative launch attribute (validates co-residency of the persistent grid)
     int prefetch_kb = 0;
     bool pair = false;   // cta_group::2: two CTAs (one cluster) per 256-row tile
     uint32_t epoch = 0;
@@ -309,9 +310,11 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     lc.stream = stream;
     cudaLaunchAttribute attrs[2];
     int na = 0;
-    attrs[na].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: in-kernel spin waits + grid barrier
-    attrs[na].val.cooperative = 1;
-    ++na;
+    if (c->coop) {
+        attrs[na].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: in-kernel spin waits + grid barrier
+        attrs[na].val.cooperative = 1;
+        ++na;
+    }
     if (c->pair) {
         attrs[na].id = cudaLaunchAttributeClusterDimension;
         attrs[na].val.clusterDim.x = 2;
@@ -422,6 +425,29 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->bn1 = env_int("FM_BN1", 256) == 128 ? 128 : 256;
     ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 8);
     ctx->dbg_flags = env_int("FM_DBG_FLAGS", 0);
+    // CTA-pair launches are NOT cooperative: Nsight Compute cannot replay a cooperative launch with cluster dimensions
+    // (driver reports LaunchFailed).  Co-residency is verified once below with cudaOccupancyMaxActiveClusters.
+    ctx->coop = env_int("FM_COOP", ctx->pair ? 0 : 1) != 0;
+    if (ctx->pair) {
+        cudaLaunchConfig_t oc;
+        memset(&oc, 0, sizeof(oc));
+        oc.gridDim = dim3(ctx->grid);
+        oc.blockDim = dim3(fm::NUM_THREADS);
+        oc.dynamicSmemBytes = (size_t)fm::SMEM_BYTES;
+        cudaLaunchAttribute oa[1];
+        oa[0].id = cudaLaunchAttributeClusterDimension;
+        oa[0].val.clusterDim.x = 2; oa[0].val.clusterDim.y = 1; oa[0].val.clusterDim.z = 1;
+        oc.attrs = oa;
+        oc.numAttrs = 1;
+        int max_clusters = 0;
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, fm::fm_moe_forward_kernel<true>, &oc);
+        if (oe != cudaSuccess || max_clusters * 2 < ctx->grid) {
+            const int got = max_clusters;
+            delete ctx;
+            return fail(FM_ECUDA, "the persistent grid of %d CTA pairs cannot be co-resident (max active clusters %d, %s)",
+                        d.num_sms / 2, got, cudaGetErrorString(oe));
+        }
+    }
     ctx->prefetch_kb = env_int("FM_PREFETCH_KB", 0);
     if (ctx->prefetch_kb < 0) ctx->prefetch_kb = 0;
     if (ctx->claim_ahead_kb < 0) ctx->claim_ahead_kb = 0;
