@@ -49,8 +49,9 @@ constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_TMEM_FULL = 2 * MAX_STAG
 constexpr int BAR_SCHED_FULL = BAR_TMEM_EMPTY + 2, BAR_SCHED_EMPTY = BAR_SCHED_FULL + NSCHED;
 constexpr int BAR_PROD_TAKE = BAR_SCHED_EMPTY + NSCHED;
 constexpr int BAR_XROWS = BAR_PROD_TAKE + NSCHED;                     // dispatch phase: bulk row load
-constexpr int NUM_BARS = BAR_XROWS + 1;                               // 29 (+1 pad to keep the ring 16-byte aligned)
-constexpr int OFF_RING = OFF_BARS + (NUM_BARS + 1) * 8;               // 16-byte aligned
+constexpr int BAR_DISP_DONE = BAR_XROWS + 1;                          // this CTA's dispatch no longer uses the stage area
+constexpr int NUM_BARS = BAR_DISP_DONE + 1;                           // 30
+constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
 constexpr int SMEM_USED = OFF_MISC + 64;
@@ -457,6 +458,9 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
 #pragma unroll
     for (int i = 0; i < 7; ++i) tot_r[i] = (tid + i * DISP_THREADS < E) ? total_s[tid + i * DISP_THREADS] : 0;
     disp_sync();
+    // from here this CTA's dispatch no longer touches the stage area: release the TMA producer (which entered its role
+    // right after the grid barrier and may already hold a tile of a REMOTE packet whose flag arrived early)
+    if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
     if (misc[0]) {  // last CTA to finish: every chunk's rows are out; publish {epoch, rows} to the owners
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
@@ -541,11 +545,21 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 const int src = blk.pkt / p.nLx, le = blk.pkt - src * p.nLx;
                 // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
                 unsigned long long f;
+                bool stale = false;
                 {
                     SpinGuard g;
-                    while (((f = ld_acquire_sys_u64(p.recv_flag + blk.pkt)) >> 32) != p.epoch)
+                    for (;;) {
+                        f = ld_acquire_sys_u64(p.recv_flag + blk.pkt);
+                        const int ahead = (int)((unsigned int)(f >> 32) - p.epoch);
+                        if (ahead == 0) break;
+                        // The source rank is already in a LATER forward: it only gets there after every real tile of
+                        // this packet has been returned to it, so whatever item of the static superset is left here
+                        // is an empty row block.
+                        if (ahead > 0) { stale = true; break; }
                         g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, blk.pkt, (unsigned int)(f >> 32), p.epoch);
+                    }
                 }
+                if (stale) continue;
                 const int cnt = (int)(f & 0xffffffffull);
                 if (local == 0 && blk.kind == 0) p.recv_cnt[blk.pkt] = cnt;
                 if (p.fused && local == 0 && blk.kind == 1 && cnt == 0)   // nothing to contribute: tell the source now
@@ -608,6 +622,7 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
     int stage = 0, phase = 0, q = 0, qphase = 0;
+    bool first = true;
     for (;;) {
         int kind = -1;
         TileInfo ti;
@@ -620,6 +635,9 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
         kind = __shfl_sync(0xffffffffu, kind, 0);
         if (kind < 0) break;
         if (lane == 0) {
+            if (first && (p.phase_mask & 1u))   // the stage area doubles as the dispatch staging buffer of this CTA
+                mbar_wait(&bars[BAR_DISP_DONE], 0, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, 901);
+            first = false;
             fence_proxy_async_global();  // rows written by generic-proxy stores (peers / other SMs) -> TMA reads
             const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
             const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
@@ -956,6 +974,7 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
             mbar_init(&bars[BAR_PROD_TAKE + i], 1);
         }
         mbar_init(&bars[BAR_XROWS], 1);
+        mbar_init(&bars[BAR_DISP_DONE], 1);
         fence_mbar_init();
     }
     if (warp == 0 && (tid & 31) == 0) {

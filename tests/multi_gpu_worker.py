@@ -40,7 +40,7 @@ def main():
         ctx = MoEContext(cfg, rank=rank, world=world, device=local, timeout_ms=20000)
         xd, wgd, wed = x.to(dev), wg.to(dev), we.to(dev)
         out = None
-        for _ in range(3):  # several launches: epoch-tagged flags, buffer reuse across forwards
+        for _ in range(int(os.environ.get("FM_MULTI_LAUNCHES", "3"))):  # several launches: epoch-tagged flags, buffer reuse
             out = ctx.forward(xd, wgd, wed)
         ctx.synchronize()
         dist.barrier()
