@@ -635,7 +635,7 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
         kind = __shfl_sync(0xffffffffu, kind, 0);
         if (kind < 0) break;
         if (lane == 0) {
-            if (first && (p.phase_mask & 1u))   // the stage area doubles as the dispatch staging buffer of this CTA
+            if (first && (p.phase_mask & 1u) && !(p.dbg_flags & 32))   // the stage area doubles as the dispatch staging buffer
                 mbar_wait(&bars[BAR_DISP_DONE], 0, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, 901);
             first = false;
             fence_proxy_async_global();  // rows written by generic-proxy stores (peers / other SMs) -> TMA reads
