@@ -131,8 +131,9 @@ def usable_cpus() -> int:
 
 
 def cpu_forward_tokens_per_s(cfg, budget_s, steps_hint=3):
-    """Plain torch CPU MoE forward (oracle/torch_moe.py) of the bench workload on the host cores.  Returns
-    (tokens/s, threads, description, seconds per step, tokens per step)."""
+    """Prepare the plain torch CPU MoE forward (oracle/torch_moe.py) of the bench workload on the host cores: runs one
+    full-size warm-up forward to size a bounded per-step sample.  Returns (torch_moe module, x sample [tokens,H], gate
+    weights, expert weights, config of the sample, tokens per step, seconds of the full-size warm-up)."""
     from oracle import torch_moe
 
     torch.set_num_threads(usable_cpus())

@@ -302,8 +302,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.dbg = c->dbg_dev;
     p.trace = c->trace_on ? c->trace : nullptr;
 
-    cudaLaunchConfig_t lc;
-    memset(&lc, 0, sizeof(lc));
+    cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(c->grid);
     lc.blockDim = dim3(fm::NUM_THREADS);
     lc.dynamicSmemBytes = (size_t)fm::SMEM_BYTES;
@@ -429,8 +428,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     // (driver reports LaunchFailed).  Co-residency is verified once below with cudaOccupancyMaxActiveClusters.
     ctx->coop = env_int("FM_COOP", ctx->pair ? 0 : 1) != 0;
     if (ctx->pair) {
-        cudaLaunchConfig_t oc;
-        memset(&oc, 0, sizeof(oc));
+        cudaLaunchConfig_t oc = {};
         oc.gridDim = dim3(ctx->grid);
         oc.blockDim = dim3(fm::NUM_THREADS);
         oc.dynamicSmemBytes = (size_t)fm::SMEM_BYTES;
@@ -718,14 +716,14 @@ static int buffer_desc(const fm_ctx_t* c, int which, const void** ptr, size_t* b
 
 FM_API int fm_buffer_bytes(const fm_ctx_t* ctx, int which, size_t* bytes) {
     if (ctx == nullptr || bytes == nullptr) return fail(FM_EINVAL, "null argument");
-    const void* p;
+    const void* p = nullptr;
     return buffer_desc(ctx, which, &p, bytes);
 }
 
 FM_API int fm_read_buffer(fm_ctx_t* ctx, int which, void* host_dst, size_t bytes) {
     if (ctx == nullptr || host_dst == nullptr) return fail(FM_EINVAL, "null argument");
-    const void* p;
-    size_t n;
+    const void* p = nullptr;
+    size_t n = 0;
     int rc = buffer_desc(ctx, which, &p, &n);
     if (rc) return rc;
     if (bytes != n) return fail(FM_EINVAL, "buffer %d holds %zu bytes, caller asked for %zu", which, n, bytes);
