@@ -281,6 +281,10 @@ def main():
         except Exception:
             traffic = None
     hbm_alg = S * H * 2 * 2 + E * H * 2 + nlx * 2 * H * P * 2 + (rows_total / world) * (2 * H + 2 * P) * 2
+    # per-GPU NVLink bytes per direction: dispatch rows out + expert outputs back, remote fraction 1 - 1/W
+    nvl_bytes = 2.0 * (rows_total / world) * (1.0 - 1.0 / world) * H * 2
+    nvl_floor_ms = nvl_bytes / 770e9 * 1e3   # measured peer-copy bandwidth of this pool (B200_PROFILING.md)
+    flop_floor_ms = flops_rank / (peaks["bf16_sustained"] * 1e12) * 1e3
     line = {
         "metric": "moe_layer_fwd_tokens_per_s", "value": world * S / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -294,7 +298,10 @@ def main():
                      "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
                      "peak_kind": "sustained cuBLAS bf16, " + peaks["source"],
                      "algorithmic_flops_per_launch": flops_rank, "algorithmic_hbm_bytes_per_launch": hbm_alg,
-                     "hbm_frac_of_measured_copy": hbm_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]},
+                     "hbm_frac_of_measured_copy": hbm_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "nvlink_bytes_per_dir_per_gpu": nvl_bytes, "nvlink_floor_ms_at_770GBs": nvl_floor_ms,
+                     "flop_floor_ms": flop_floor_ms,
+                     "frac_of_slower_floor": max(nvl_floor_ms, flop_floor_ms) / ms},
         "e2e": {"value": world * S / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": S * H * 2,
                 "d2h_bytes_per_step": S * H * 2, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "api": "MoEContext.forward_host -> fm_moe_forward_host (pinned host activations, device-resident weights)"},
