@@ -33,3 +33,35 @@ def test_token_sweep_point_32_experts():
     ref = run_oracle(cfg, x, wg, we)
     _compare(cfg, got, ref)
     assert (np.minimum(got["counts"], cfg.EC) == np.minimum(ref.counts, cfg.EC)).all()
+
+
+def test_module_wrapper_with_bias_and_routing_outputs():
+    """flashmoe_b200.layer.FlashMoELayer: caller-owned parameters, bias + GELU, routing tables returned."""
+    import torch
+
+    from flashmoe_b200.layer import FlashMoELayer
+    from oracle import moe_oracle as mo
+    from tests.util import check_output, check_topk
+
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=256, hidden_size=256, intermediate_size=512, hidden_act=1)
+    torch.manual_seed(5)
+    layer = FlashMoELayer(cfg, bias=True)
+    layer.bias_up.data.normal_(0, 0.1)
+    layer.bias_down.data.normal_(0, 0.1)
+    x = torch.randn(1, cfg.S, cfg.H, device=layer.ctx.device).bfloat16()
+    res = layer(x, return_routing=True)
+    assert res.out.shape == x.shape and res.topk_idx.shape == (cfg.S, 2) and res.topk_weight.dtype == torch.bfloat16
+    ref = run_oracle(cfg, x.cpu(), layer.gate_weight.data.cpu(), layer.expert_weight.data.cpu(), layer.bias_up.data.cpu(),
+                     layer.bias_down.data.cpu())
+    mism = check_topk(res.topk_idx.numpy(), ref)
+    check_output(mo.to_bits(res.out.cpu().reshape(cfg.S, cfg.H)), ref.out, rows_ok=~mism)
+    assert (res.slot.numpy()[~mism] == ref.slot[~mism]).all()
+    layer.ctx.close()
+
+
+def test_run_moe_entry_point_single_gpu():
+    """flashmoe.run_moe(): launcher -> worker -> _C on the compiled configuration, like the reference's quick start."""
+    import flashmoe
+
+    res = flashmoe.run_moe(n_processes=1)
+    assert "FlashMoE forward pass took" in res.stdout and "Completed! Output: torch.Size([1, 4096, 1024])" in res.stdout
