@@ -2,19 +2,26 @@
 //
 // One launch = one MoE layer forward on this rank (reference: flashmoe::moe::forward, csrc/include/flashmoe/moe/moe.cuh:77-144):
 //
-//   phase G  gate      x.Wg^T -> online softmax -> top-k -> capacity slots          (reference moe/gate.cuh:473-720)
-//            grid barrier (the only one, like the reference's gate.cuh:761)
-//   phase D  dispatch  token rows -> owner rank's receive buffer over NVLink + flag  (reference os/packet.cuh:21-286)
-//   phase F  expert FFN  persistent tcgen05 tile loop: GEMM0(+bias+act) -> h, GEMM1(+bias) -> source rank's return
-//            buffer + per-row-block flag                                            (reference os/processor/processor.cuh:340-468,
+//   prologue  mbarriers + TMEM allocation for the later phases (off the critical path)
+//   phase G   router    x.Wg^T -> online softmax -> top-k -> capacity slots         (reference moe/gate.cuh:473-720)
+//             grid barrier (the only one, like the reference's gate.cuh:761)
+//   phase D   dispatch  token rows -> owner rank's receive buffer over NVLink (TMA bulk copies) + one flag per expert
+//                                                                                    (reference os/packet.cuh:21-286)
+//   phase F   expert FFN  persistent tcgen05 tile loop over CTA pairs: GEMM0(+bias+act) -> h, GEMM1(+bias) -> for k <= 2
+//             scaled and ADDED straight into the token's output row on the source rank (REDG.BF16x8 over peer memory),
+//             otherwise stored to the source rank's return buffer + per-row-block flag
+//                                                                                    (reference os/processor/processor.cuh:340-468,
 //                                                                                    685-750; the OS CTA of os/os.cuh, scheduler.cuh,
 //                                                                                    subscriber.cuh is replaced by an atomic tile
-//                                                                                    claim + flag waits inside every CTA)
-//   phase C  combine   per token: gather the k returned rows, scale, bf16-accumulate (reference processor.cuh:27-205)
+//                                                                                    claim + flag waits in one warp per CTA pair)
+//   phase C   completion: wait for the experts' done flags (fused path) or gather-combine the k returned rows per token
+//                                                                                    (reference processor.cuh:27-205)
 //
-// CTA = 256 threads, one CTA per SM, all co-resident (cooperative launch).  In phase F the warps specialise:
-// warp 0 = TMA producer, warp 1 = tcgen05.mma issuer, warp 2 = TMEM allocator, warp 3 = tile claimer, warps 4-7 = epilogue
-// (TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced 16-byte global / peer stores).
+// CTA = 256 threads, one CTA per SM, all co-resident (74 clusters of 2; co-residency is checked on the host with
+// cudaOccupancyMaxActiveClusters).  After the grid barrier the warps specialise: warp 0 = TMA producer, warp 1 = tcgen05.mma
+// issuer (leader CTA of the pair), warp 3 = tile scheduler (leader CTA), warps 2 and 4-7 = dispatch, then warps 4-7 =
+// epilogue (TMEM -> registers -> bias/activation/combine scaling -> bf16 -> smem transpose -> 16-byte global / peer stores
+// or adds); warp 2 owns the TMEM allocation.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -34,8 +41,9 @@ constexpr int NSCHED = 4;
 constexpr int NUM_THREADS = 256;
 constexpr int NUM_WARPS = NUM_THREADS / 32;
 constexpr int EPI_WARP0 = 4;   // warps 4..7 (warp % 4 selects the TMEM lane quarter)
-constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators
-constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [7] tiles, [16+i] tile i ready, [64+i] tile i stored
+constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators per CTA (double-buffered against the epilogue)
+constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..15] sub-phase stamps, [16+i] tile i ready,
+                                 // [64+i] tile i stored, [112+i] tile i claimed (i < 8), [120..124] epilogue of tile 2
 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                  // 16 KiB
 constexpr int PIPE_BYTES = 196608;                                    // 4 x 48 KiB (solo) = 6 x 32 KiB (CTA pair)
@@ -477,10 +485,11 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
 }
 
 // ============================================================================================================
-// Phase F: expert FFN.  Work items (global order, claimed with one atomic counter):
-//   for packets in the order (own rank first, then rank+1, ...): GEMM0 tiles of packet j, then GEMM1 tiles of packet
-//   j-1 (one packet of lag so the h row-block a GEMM1 tile needs is normally complete when it is claimed).
-//   item -> (row block m fastest, column tile n).  A GEMM1 tile waits for g0_done[pkt][m] == TN0.
+// Phase F: expert FFN.  Work items (global order, claimed with one atomic counter by the pair's scheduler warp):
+//   packets in the order (own rank first, then rank+1, ...); all GEMM0 blocks, then the GEMM1 blocks (host knob FM_G1_LAG
+//   interleaves them with a lag instead).  item -> (row-block pair m fastest, column tile n).  The item list is a static
+//   superset: row blocks beyond the packet's row count are skipped once the packet flag is known.  A GEMM1 tile waits for
+//   g0_done[pkt][m] == TN0 (both row blocks of the pair).
 // ============================================================================================================
 struct TileInfo {     // 64 bytes, written by the (leader's) scheduler warp, read by producer / MMA / epilogue warps
     int kind;         // 0 GEMM0, 1 GEMM1, -1 stop
