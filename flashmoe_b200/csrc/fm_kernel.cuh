@@ -363,10 +363,10 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
 
 // ============================================================================================================
 // Phase D: dispatch (after the grid barrier).  slot = (selections of e by lower chunks) + rank in chunk; kept iff
-// slot < EC (gate.cuh:713-717).  Each warp copies whole token rows with 16-byte accesses straight into the owner
-// rank's receive buffer (peer-mapped, NVLink) -- the reference's P2P branch (os/packet.cuh:114-116,151-166).
+// slot < EC (gate.cuh:713-717).  Whole token rows go straight into the owner rank's receive buffer (peer-mapped, NVLink)
+// -- the reference's P2P branch (os/packet.cuh:114-116,151-166) -- as TMA bulk copies staged through shared memory.
 // The last CTA to finish publishes one 8-byte flag {epoch, rows} per expert (os/packet.cuh:214-237; a flag is
-// also sent for 0 rows, like the reference's "noop" signal).
+// also sent for 0 rows, like the reference's "noop" signal).  Runs on warps 2,4-7 only (see the kernel body).
 // ============================================================================================================
 constexpr int DISP_THREADS = 160;   // warps 2,4,5,6,7; warps 0,1,3 are already in their FFN roles (producer / MMA / scheduler)
 __device__ __forceinline__ void disp_sync() { asm volatile("bar.sync 2, 160;" ::: "memory"); }
@@ -1021,7 +1021,8 @@ __device__ __forceinline__ void ffn_teardown(const FmParams& p, uint8_t* smem) {
 }
 
 // ============================================================================================================
-// Phase C: combine.  For token t with picks (e_j, slot_j):
+// Phase C: combine (gather path: k > 2 or FM_FUSED_COMBINE=0; the default for k <= 2 is the fused GEMM1 epilogue +
+// finish_fused below).  For token t with picks (e_j, slot_j):
 //   k > 1: out[t,c] = bf16-accumulate over kept j of rne( p~_j * rne( y_j[c] / mCw ) )   (processor.cuh:110-169)
 //   k = 1: out[t,:] = y_0 (no scaling), zeros if dropped                                  (processor.cuh:170-203)
 // Deterministic gather (no atomics, no zero-fill pass); for k == 2 it equals the reference's atomicAdd result
