@@ -41,7 +41,7 @@ class FmConfig(ctypes.Structure):
 class FmDims(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in (
         "S", "H", "E", "P", "PX", "element_size", "k", "EC", "pEC", "TCM", "world", "rank", "num_local_experts",
-        "num_sms", "smem_bytes")]
+        "num_sms", "smem_bytes", "grid")]
 
 
 _lib: Optional[ctypes.CDLL] = None

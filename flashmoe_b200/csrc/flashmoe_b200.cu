@@ -109,7 +109,9 @@ struct fm_ctx {
     bool pair = false;   // cta_group::2: two CTAs (one cluster) per 256-row tile
     uint32_t epoch = 0;
     unsigned long long bar_count = 0;
-    unsigned long long timeout_ns = 10ull * 1000ull * 1000ull * 1000ull;
+    // in-kernel waits give up after this long (fm_set_timeout_ms): generous by default so that ordinary rank skew (a peer
+    // still loading data, compiling, paused in a debugger) is not turned into a trap -- see fm_ptx.cuh SpinGuard
+    unsigned long long timeout_ns = 120ull * 1000ull * 1000ull * 1000ull;
     uint64_t launches = 0;
     // device buffers
     int* topk_idx = nullptr;
@@ -119,7 +121,7 @@ struct fm_ctx {
     int* counts = nullptr;
     __nv_bfloat16* gate_out = nullptr;
     int* chunk_counts = nullptr;
-    unsigned int* ctrl = nullptr;  // [0] disp_done, [1] claim, [2..3] grid barrier (u64)
+    unsigned int* ctrl = nullptr;  // [0] unused, [1] claim, [2..3] grid barrier (u64)
     unsigned int* g0_done = nullptr;
     unsigned int* g1_done = nullptr;
     int* recv_cnt = nullptr;
@@ -131,7 +133,7 @@ struct fm_ctx {
     void* symm = nullptr;
     bool symm_external = false;
     size_t symm_bytes = 0, off_recv_x = 0, off_ret_y = 0, off_recv_flag = 0, off_ret_flag = 0;
-    size_t off_recv_meta = 0, off_out_acc = 0, off_done_flag = 0;
+    size_t off_recv_meta = 0, off_out_acc = 0, off_done_flag = 0, off_recv_rows = 0;
     bool fused = false;   // GEMM1 epilogue adds straight into the source rank's output (no return buffer / gather)
     unsigned int* pkt_done = nullptr;
     void* peer_base[FM_MAX_WORLD] = {};
@@ -206,6 +208,7 @@ void set_peer_pointers(const fm_ctx* c, fm::FmParams& p) {
         p.peer_recv_x[r] = reinterpret_cast<__nv_bfloat16*>(b + c->off_recv_x);
         p.peer_ret_y[r] = reinterpret_cast<__nv_bfloat16*>(b + c->off_ret_y);
         p.peer_recv_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_recv_flag);
+        p.peer_recv_rows[r] = reinterpret_cast<unsigned int*>(b + c->off_recv_rows);
         p.peer_ret_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_ret_flag);
         p.peer_recv_meta[r] = reinterpret_cast<uint4*>(b + c->off_recv_meta);
         p.peer_done_flag[r] = reinterpret_cast<unsigned long long*>(b + c->off_done_flag);
@@ -218,7 +221,8 @@ int check_kernel_status(fm_ctx* c) {
         static const char* names[] = {"none", "smem-full mbarrier", "smem-empty mbarrier", "tmem-full mbarrier",
                                       "tmem-empty mbarrier", "sched-full mbarrier", "sched-empty mbarrier",
                                       "grid barrier", "dispatch flag (packet never arrived)", "GEMM0 row-block counter",
-                                      "return flag (expert output never arrived)"};
+                                      "return flag (expert output never arrived)",
+                                      "dispatch row acknowledgement (rows of a packet never arrived)", "publisher mbarrier"};
         const fm::DebugRecord r = *c->dbg_host;
         const char* nm = r.code < sizeof(names) / sizeof(names[0]) ? names[r.code] : "unknown";
         return fail(FM_EKERNEL,
@@ -234,6 +238,13 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     if (c == nullptr) return fail(FM_EINVAL, "null context");
     if (x == nullptr || gate_w == nullptr || expert_w == nullptr || out == nullptr)
         return fail(FM_EINVAL, "x, gate_w, expert_w and out must be non-null device pointers");
+    {   // TMA tensor maps, cp.async.bulk row copies and the 16-byte vector accesses all need 16-byte aligned bases
+        const void* ptrs[] = {x, gate_w, expert_w, bias_up, bias_down, out};
+        const char* names[] = {"x", "gate_w", "expert_w", "bias_up", "bias_down", "out"};
+        for (int i = 0; i < 6; ++i)
+            if (reinterpret_cast<uintptr_t>(ptrs[i]) % 16)
+                return fail(FM_EINVAL, "%s must be 16-byte aligned (got %p)", names[i], ptrs[i]);
+    }
     if (!c->attached) return fail(FM_ESTATE, "peers not attached: call fm_symm_attach_ipc/ptrs before fm_moe_forward");
     if ((phase_mask & 1u) == 0u && c->d.world != 1) return fail(FM_EINVAL, "partial-phase launches are single-rank only");
     if ((phase_mask & 1u) == 0u && c->epoch == 0) return fail(FM_ESTATE, "no previous routing to reuse");
@@ -267,13 +278,13 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.TN0 = c->TN0; p.TN1 = c->TN1; p.tpc = c->tpc; p.num_pkts = c->num_pkts; p.num_blocks = c->num_blocks;
     p.total_items = c->total_items;
     p.bn[0] = c->bn0; p.bn[1] = c->bn1; p.claim_ahead_kb = c->claim_ahead_kb; p.dbg_flags = c->dbg_flags; p.prefetch_kb = c->prefetch_kb;
-    if (phase_mask & 1u) {
-        c->epoch += 1;
-        c->bar_count += (unsigned long long)c->grid;
-    }
-    p.epoch = c->epoch;
+    // the epoch and the grid-barrier target advance only when the launch has been accepted (see below): a failed launch
+    // must not leave the host ahead of the device counter and of the peers
+    const uint32_t epoch = c->epoch + ((phase_mask & 1u) ? 1u : 0u);
+    const unsigned long long bar_count = c->bar_count + ((phase_mask & 1u) ? (unsigned long long)c->grid : 0ull);
+    p.epoch = epoch;
     p.phase_mask = phase_mask;
-    p.bar_target = c->bar_count;
+    p.bar_target = bar_count;
     p.timeout_ns = c->timeout_ns;
     p.x = static_cast<const __nv_bfloat16*>(x);
     p.wg = static_cast<const __nv_bfloat16*>(gate_w);
@@ -282,7 +293,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.out = static_cast<__nv_bfloat16*>(out);
     p.topk_idx = c->topk_idx; p.topk_w = c->topk_w; p.mcw = c->mcw; p.slot = c->slot; p.counts = c->counts;
     p.gate_out = c->gate_out; p.chunk_counts = c->chunk_counts;
-    p.disp_done = c->ctrl; p.claim = c->ctrl + 1;
+    p.claim = c->ctrl + 1;
     p.grid_bar = reinterpret_cast<unsigned long long*>(c->ctrl + 2);
     p.g0_done = c->g0_done; p.g1_done = c->g1_done; p.recv_cnt = c->recv_cnt; p.blocks = c->blocks;
     p.hidden = c->hidden;
@@ -290,6 +301,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     p.recv_x = reinterpret_cast<__nv_bfloat16*>(sb + c->off_recv_x);
     p.ret_y = reinterpret_cast<__nv_bfloat16*>(sb + c->off_ret_y);
     p.recv_flag = reinterpret_cast<unsigned long long*>(sb + c->off_recv_flag);
+    p.recv_rows = reinterpret_cast<unsigned int*>(sb + c->off_recv_rows);
     p.ret_flag = reinterpret_cast<unsigned long long*>(sb + c->off_ret_flag);
     set_peer_pointers(c, p);
     p.fused = c->fused ? 1 : 0;
@@ -325,6 +337,8 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     lc.numAttrs = na;
     if (c->pair) FM_CUDA(cudaLaunchKernelEx(&lc, fm::fm_moe_forward_kernel<true>, p));
     else FM_CUDA(cudaLaunchKernelEx(&lc, fm::fm_moe_forward_kernel<false>, p));
+    c->epoch = epoch;
+    c->bar_count = bar_count;
     c->launches += 1;
     return FM_OK;
 }
@@ -384,6 +398,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     if (!coop) return fail(FM_ECUDA, "device does not support cooperative launch");
     d.num_sms = prop.multiProcessorCount;
     d.smem_bytes = fm::SMEM_BYTES;
+    d.grid = prop.multiProcessorCount;
 
     FM_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(&fm::fm_moe_forward_kernel<false>),
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, fm::SMEM_BYTES));
@@ -408,6 +423,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         const char* f = getenv("FM_FUSED_COMBINE");
         ctx->fused = ((f != nullptr && *f) ? atoi(f) != 0 : true) && d.k <= 2;
         if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
+        ctx->d.grid = ctx->grid;
     }
     ctx->tpc = ceil_div(d.S, ctx->grid);
     if ((long long)ctx->tpc * d.k > fm::G_SEL_MAX) {
@@ -424,9 +440,14 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->bn1 = env_int("FM_BN1", 256) == 128 ? 128 : 256;
     ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 8);
     ctx->dbg_flags = env_int("FM_DBG_FLAGS", 0);
-    // CTA-pair launches are NOT cooperative: Nsight Compute cannot replay a cooperative launch with cluster dimensions
-    // (driver reports LaunchFailed).  Co-residency is verified once below with cudaOccupancyMaxActiveClusters.
-    ctx->coop = env_int("FM_COOP", ctx->pair ? 0 : 1) != 0;
+    // The persistent grid spins on flags, counters and one grid barrier, so every CTA must be resident: the launch is
+    // cooperative (the driver then refuses to start it unless the whole grid fits, also next to other work on the GPU).
+    // One exception: Nsight Compute cannot replay a cooperative launch that also has cluster dimensions (the driver
+    // reports LaunchFailed), so under a CUDA injection profiler -- or with FM_COOP=0 -- the attribute is dropped and
+    // co-residency rests on the cudaOccupancyMaxActiveClusters check below plus exclusive use of the GPU.
+    const bool under_profiler = getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                                getenv("NSIGHT_CUDA_DEBUGGER") != nullptr;
+    ctx->coop = env_int("FM_COOP", (ctx->pair && under_profiler) ? 0 : 1) != 0;
     if (ctx->pair) {
         cudaLaunchConfig_t oc = {};
         oc.gridDim = dim3(ctx->grid);
@@ -519,10 +540,13 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
 
     // symmetric slab: [recv_x | ret_y | recv_flag | ret_flag]  (reference heap + flags, bootstrap.cuh:348-362)
     size_t off = 0;
+    // the return buffer + per-row-block return flags exist only on the gather-combine path (the fused path adds
+    // straight into the token's output row)
     ctx->off_recv_x = off; off = align_up(off + (size_t)ctx->num_pkts * d.pEC * d.H * 2, 1024);
-    ctx->off_ret_y = off;  off = align_up(off + (size_t)d.E * d.pEC * d.H * 2, 1024);
+    ctx->off_ret_y = off;  off = align_up(off + (ctx->fused ? 0 : (size_t)d.E * d.pEC * d.H * 2), 1024);
     ctx->off_recv_flag = off; off = align_up(off + (size_t)ctx->num_pkts * 8, 1024);
-    ctx->off_ret_flag = off;  off = align_up(off + (size_t)d.E * d.TCM * 8, 1024);
+    ctx->off_recv_rows = off; off = align_up(off + (size_t)2 * ctx->num_pkts * d.TCM * 4, 1024);
+    ctx->off_ret_flag = off;  off = align_up(off + (ctx->fused ? 0 : (size_t)d.E * d.TCM * 8), 1024);
     ctx->off_recv_meta = off; off = align_up(off + (size_t)ctx->num_pkts * d.pEC * 16, 1024);
     ctx->off_done_flag = off; off = align_up(off + (size_t)d.E * 8, 1024);
     ctx->off_out_acc = off;   off = align_up(off + (world > 1 ? (size_t)d.S * d.H * 2 : 0), 1024);
@@ -705,7 +729,9 @@ static int buffer_desc(const fm_ctx_t* c, int which, const void** ptr, size_t* b
         case FM_BUF_COUNTS: *ptr = c->counts; *bytes = (size_t)d.E * 4; break;
         case FM_BUF_RECV_X: *ptr = sb + c->off_recv_x; *bytes = (size_t)c->num_pkts * d.pEC * d.H * 2; break;
         case FM_BUF_HIDDEN: *ptr = c->hidden; *bytes = (size_t)c->num_pkts * d.pEC * d.P * 2; break;
-        case FM_BUF_RET_Y: *ptr = sb + c->off_ret_y; *bytes = (size_t)d.E * d.pEC * d.H * 2; break;
+        case FM_BUF_RET_Y:
+            if (c->fused) return fail(FM_EINVAL, "the return buffer does not exist on the fused-combine path (FM_FUSED_COMBINE=0 keeps it)");
+            *ptr = sb + c->off_ret_y; *bytes = (size_t)d.E * d.pEC * d.H * 2; break;
         case FM_BUF_GATE_OUT: *ptr = c->gate_out; *bytes = (size_t)d.S * d.E * 2; break;
         case FM_BUF_RECV_CNT: *ptr = c->recv_cnt; *bytes = (size_t)c->num_pkts * 4; break;
         case FM_BUF_TRACE: *ptr = c->trace; *bytes = (size_t)c->grid * fm::TRACE_SLOTS * 8; break;

@@ -17,11 +17,13 @@
 //   phase C   completion: wait for the experts' done flags (fused path) or gather-combine the k returned rows per token
 //                                                                                    (reference processor.cuh:27-205)
 //
-// CTA = 256 threads, one CTA per SM, all co-resident (74 clusters of 2; co-residency is checked on the host with
-// cudaOccupancyMaxActiveClusters).  After the grid barrier the warps specialise: warp 0 = TMA producer, warp 1 = tcgen05.mma
-// issuer (leader CTA of the pair), warp 3 = tile scheduler (leader CTA), warps 2 and 4-7 = dispatch, then warps 4-7 =
-// epilogue (TMEM -> registers -> bias/activation/combine scaling -> bf16 -> smem transpose -> 16-byte global / peer stores
-// or adds); warp 2 owns the TMEM allocation.
+// CTA = 384 threads, one CTA per SM, all co-resident (74 clusters of 2; cooperative launch, and co-residency is checked on
+// the host with cudaOccupancyMaxActiveClusters).  After the grid barrier the warps specialise: warp 0 = TMA producer,
+// warp 1 = tcgen05.mma issuer (leader CTA of the pair), warp 3 = tile scheduler (leader CTA), warps 2 and 4-11 = dispatch,
+// then warps 4-11 = epilogue (TMEM -> registers -> bias/activation/combine scaling -> bf16 -> swizzled smem transpose ->
+// 16-byte global / peer stores or adds; two warps per TMEM lane quarter, each draining half of the tile's columns) and
+// warp 2 = publisher (the release fence + counter / flag traffic of every finished tile, off the epilogue warps' critical
+// path); warp 2 also owns the TMEM allocation.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -38,9 +40,10 @@ constexpr int BLOCK_N = 256;   // max output columns per tile (one tcgen05.mma N
 constexpr int BLOCK_K = 64;    // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NSCHED = 4;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;
 constexpr int NUM_WARPS = NUM_THREADS / 32;
-constexpr int EPI_WARP0 = 4;   // warps 4..7 (warp % 4 selects the TMEM lane quarter)
+constexpr int EPI_WARP0 = 4;   // warps 4..11: warp % 4 selects the TMEM lane quarter, (warp - 4) / 4 the column half
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators per CTA (double-buffered against the epilogue)
 constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..15] sub-phase stamps, [16+i] tile i ready,
                                  // [64+i] tile i stored, [112+i] tile i claimed (i < 8), [120..124] epilogue of tile 2
@@ -48,23 +51,27 @@ constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..15] sub-ph
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                  // 16 KiB
 constexpr int PIPE_BYTES = 196608;                                    // 4 x 48 KiB (solo) = 6 x 32 KiB (CTA pair)
 constexpr int MAX_STAGES = 6;
-constexpr int EPI_ROW_BYTES = 144;                                    // 128 B of payload + 16 B pad (bank spread)
-constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;
+constexpr int EPI_ROW_BYTES = 128;                                    // 64 bf16; 16-byte pieces XOR-swizzled by (row & 7)
+constexpr int EPI_WARP_BYTES = 32 * EPI_ROW_BYTES;                    // 4 KiB per epilogue warp
 constexpr int OFF_EPI = PIPE_BYTES;                                   // 196608
-constexpr int OFF_BARS = OFF_EPI + 4 * EPI_WARP_BYTES;                // 215040
-// barriers: full[6] empty[6] tmem_full[2] tmem_empty[2] sched_full[4] sched_empty[4] prod_take[4]
+constexpr int OFF_BARS = OFF_EPI + NUM_EPI_WARPS * EPI_WARP_BYTES;    // 229376
+// barriers: full[6] empty[6] tmem_full[2] tmem_empty[2] sched_full[4] sched_empty[4] prod_take[4] xrows disp_done
+//           pub_full[2] pub_empty[2]
 constexpr int BAR_FULL = 0, BAR_EMPTY = MAX_STAGES, BAR_TMEM_FULL = 2 * MAX_STAGES, BAR_TMEM_EMPTY = BAR_TMEM_FULL + 2;
 constexpr int BAR_SCHED_FULL = BAR_TMEM_EMPTY + 2, BAR_SCHED_EMPTY = BAR_SCHED_FULL + NSCHED;
 constexpr int BAR_PROD_TAKE = BAR_SCHED_EMPTY + NSCHED;
 constexpr int BAR_XROWS = BAR_PROD_TAKE + NSCHED;                     // dispatch phase: bulk row load
 constexpr int BAR_DISP_DONE = BAR_XROWS + 1;                          // this CTA's dispatch no longer uses the stage area
-constexpr int NUM_BARS = BAR_DISP_DONE + 1;                           // 30
+constexpr int BAR_PUB_FULL = BAR_DISP_DONE + 1;                       // epilogue warps -> publisher: tile's stores issued
+constexpr int BAR_PUB_EMPTY = BAR_PUB_FULL + 2;                       // publisher -> epilogue warps: slot consumed
+constexpr int NUM_BARS = BAR_PUB_EMPTY + 2;                           // 34
 constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
 constexpr int SMEM_USED = OFF_MISC + 64;
 constexpr int SMEM_BYTES = SMEM_USED + 1024;                          // + slack for manual 1 KiB alignment
 static_assert(OFF_RING % 16 == 0, "ring entries are copied with 16-byte accesses");
+static_assert(SMEM_BYTES <= 232448, "227 KiB of dynamic shared memory per CTA");
 
 template <bool PAIR>
 struct PipeCfg {   // solo: one CTA per 128x256 tile; pair: two CTAs share one 256x256 tile (cta_group::2)
@@ -80,9 +87,9 @@ constexpr int G_OFF_LOGIT = 65536;       // f32  [TS][E+1]          <= 64 KiB
 constexpr int G_LOGIT_BYTES = 65536;
 constexpr int G_OFF_SEL = 131072;        // int16 sel_e[tpc*k] then int32 rank[tpc*k]   <= 48 KiB
 constexpr int G_SEL_MAX = 8192;          // max tpc*k
-constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E] + total[E]   <= 8 KiB (E <= 1024)
+constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E] + total[E] + own[E]   <= 12 KiB (E <= 1024)
 constexpr int G_XROWS_BYTES = 131072;       // dispatch: staged token rows (reuses the Wg / logits scratch)
-static_assert(G_OFF_BASE + 8192 <= OFF_EPI, "gate scratch must fit in the stage area");
+static_assert(G_OFF_BASE + 12288 <= OFF_EPI, "gate scratch must fit in the stage area");
 
 struct TileBlock {  // one contiguous run of work items: all tiles of one GEMM of one packet
     int kind;       // 0 = GEMM0 (x.W_up^T), 1 = GEMM1 (h.W_down^T)
@@ -101,7 +108,9 @@ struct FmParams {
     int bn[2];          // tile width of GEMM0 / GEMM1 (128 or 256)
     int claim_ahead_kb; // the scheduler claims the next tile when this many k-blocks of the current one remain
     int prefetch_kb;    // L2 prefetch distance of the TMA producer in k-blocks (0 = off)
-    int dbg_flags;      // experiments only: bit0 = skip TMA loads, bit1 = skip MMA issue (results are garbage)
+    int dbg_flags;      // experiments only (results are garbage for bits 0-3): bit0 = skip all TMA loads, bit1 = skip MMA
+                        // issue, bit2 = skip the A loads, bit3 = skip the B loads, bit4 = partner CTA's producer also
+                        // arrives on the leader's `full` barrier (the round-1 handshake), bit5 = ignore BAR_DISP_DONE
     unsigned int epoch, phase_mask;
     unsigned long long bar_target, timeout_ns;
     const __nv_bfloat16 *x, *wg, *b_up, *b_down;
@@ -113,7 +122,6 @@ struct FmParams {
     int* counts;               // [E]
     __nv_bfloat16* gate_out;   // [S,E]
     int* chunk_counts;         // [grid, E]
-    unsigned int* disp_done;   // [1]
     unsigned int* claim;       // [1]
     unsigned int* g0_done;     // [num_pkts, TCM]
     unsigned int* g1_done;     // [num_pkts, TCM]
@@ -122,11 +130,14 @@ struct FmParams {
     const TileBlock* blocks;   // [num_blocks + 1] (sentinel start = total_items)
     __nv_bfloat16* hidden;     // [W*nLx*pEC, P]
     __nv_bfloat16* recv_x;     // local symmetric: [W, nLx, pEC, H]
-    unsigned long long* recv_flag;  // [W, nLx]
+    unsigned long long* recv_flag;  // [W, nLx]  {epoch, rows}: published as soon as the source rank knows the count
+    unsigned int* recv_rows;   // local symmetric [2, W*nLx, TCM]: rows of row block b of packet (src, le) that have landed,
+                               // indexed by epoch parity (the other parity is zeroed by CTA 0 during this launch)
     __nv_bfloat16* ret_y;      // [E, pEC, H]
     unsigned long long* ret_flag;   // [E, TCM]
     __nv_bfloat16* peer_recv_x[FM_MAX_WORLD];
     unsigned long long* peer_recv_flag[FM_MAX_WORLD];
+    unsigned int* peer_recv_rows[FM_MAX_WORLD];
     __nv_bfloat16* peer_ret_y[FM_MAX_WORLD];
     unsigned long long* peer_ret_flag[FM_MAX_WORLD];
     // fused GEMM1 -> combine path (fused != 0): the GEMM1 epilogue scales each row and adds it straight into the
@@ -344,18 +355,26 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         __syncthreads();
     }
     if (tid == 0) trace_stamp(p, 12);
-    // position of every (token, pick) among this chunk's selections of the same expert, ascending token order:
-    // one thread per entry counts the equal selections before it (warp-broadcast smem reads); totals by smem atomics
+    // position of every (token, pick) among this chunk's selections of the same expert, ascending (token, pick) order.
+    // One warp walks the entries 32 at a time: lanes holding the same expert find each other with match.any, the rank
+    // inside the group is a popcount, the running per-expert count lives in shared memory (O(n) instead of O(n^2);
+    // the 64k-token sweep point has 886 entries per CTA).
     int* cnt_s = reinterpret_cast<int*>(smem + G_OFF_BASE);
     for (int e = tid; e < E; e += NUM_THREADS) cnt_s[e] = 0;
     __syncthreads();
     const int n_ent = n_tok * k;
-    for (int i = tid; i < n_ent; i += NUM_THREADS) {
-        const int16_t e = sel_e[i];
-        int r = 0;
-        for (int j = 0; j < i; ++j) r += (sel_e[j] == e) ? 1 : 0;
-        rank_s[i] = r;
-        atomicAdd(&cnt_s[e], 1);
+    if (warp == 0) {
+        for (int i0 = 0; i0 < n_ent; i0 += 32) {
+            const int i = i0 + lane;
+            const bool valid = i < n_ent;
+            const int e = valid ? (int)sel_e[i] : (E + lane);        // invalid lanes get unique keys
+            const unsigned int same = __match_any_sync(0xffffffffu, e);
+            const unsigned int before = same & ((1u << lane) - 1u);
+            if (valid) rank_s[i] = cnt_s[e] + __popc(before);
+            __syncwarp();
+            if (valid && before == 0u) cnt_s[e] += __popc(same);    // one lane per distinct expert of the group
+            __syncwarp();
+        }
     }
     __syncthreads();
     for (int e = tid; e < E; e += NUM_THREADS) p.chunk_counts[(size_t)blockIdx.x * E + e] = cnt_s[e];
@@ -365,23 +384,28 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
 // Phase D: dispatch (after the grid barrier).  slot = (selections of e by lower chunks) + rank in chunk; kept iff
 // slot < EC (gate.cuh:713-717).  Whole token rows go straight into the owner rank's receive buffer (peer-mapped, NVLink)
 // -- the reference's P2P branch (os/packet.cuh:114-116,151-166) -- as TMA bulk copies staged through shared memory.
-// The last CTA to finish publishes one 8-byte flag {epoch, rows} per expert (os/packet.cuh:214-237; a flag is
-// also sent for 0 rows, like the reference's "noop" signal).  Runs on warps 2,4-7 only (see the kernel body).
+// Signalling (os/packet.cuh:214-237 sends one {rows, tiles, seq} word per (source, expert) once the LAST of its dispatch
+// CTAs is done): here the 8-byte {epoch, rows} flag is published as soon as the count is known -- right after the
+// prefix pass, before any row moves (also for 0 rows, like the reference's "noop" signal) -- and the data itself is
+// acknowledged per 128-row block: every CTA adds the number of rows it has landed in block b of packet (me, e) to the
+// owner's arrival counter recv_rows[epoch parity][pkt][b] with a release at system scope.  A GEMM0 tile starts when ITS
+// row blocks are complete, not when the slowest CTA of the source rank has finished.
+// Runs on warps 2, 4-11 only (see the kernel body).
 // ============================================================================================================
-constexpr int DISP_THREADS = 160;   // warps 2,4,5,6,7; warps 0,1,3 are already in their FFN roles (producer / MMA / scheduler)
-__device__ __forceinline__ void disp_sync() { asm volatile("bar.sync 2, 160;" ::: "memory"); }
+constexpr int DISP_THREADS = 288;   // warps 2, 4..11; warps 0, 1, 3 are already in their FFN roles (producer / MMA / scheduler)
+__device__ __forceinline__ void disp_sync() { asm volatile("bar.sync 2, 288;" ::: "memory"); }
 
 __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tid = (warp == 2 ? 0 : (warp - 3) * 32) + lane;   // 0..159 within the dispatch subset
+    const int tid = (warp == 2 ? 0 : (warp - 3) * 32) + lane;   // 0..287 within the dispatch subset
     const int E = p.E, H = p.H, k = p.k, G = gridDim.x;
     const int16_t* sel_e = reinterpret_cast<const int16_t*>(smem + G_OFF_SEL);
     const int* rank_s = reinterpret_cast<const int*>(smem + G_OFF_SEL + G_SEL_MAX * 2);
     int* base_s = reinterpret_cast<int*>(smem + G_OFF_BASE);        // selections of e by lower chunks
     int* total_s = base_s + 1024;                                    // selections of e by all chunks
-    unsigned int* misc = reinterpret_cast<unsigned int*>(smem + OFF_MISC);
+    int* own_s = base_s + 2048;                                      // selections of e by this chunk
 
-    // one pass over chunk_counts [G, E] gives both the prefix (lower chunks) and the totals every CTA may have to publish
+    // one pass over chunk_counts [G, E] gives the prefix (lower chunks), this chunk's own counts and the totals
     for (int e = tid; e < E; e += DISP_THREADS) { base_s[e] = 0; total_s[e] = 0; }
     disp_sync();
     {
@@ -391,6 +415,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         for (int i = tid; i < n; i += DISP_THREADS) {
             const int e = i % E;
             const int v = p.chunk_counts[i];
+            if (i >= nb && i < nb + E) own_s[e] = v;
             if (fixed_e) { part_t += v; if (i < nb) part_b += v; cur_e = e; }
             else if (v != 0) { atomicAdd(&total_s[e], v); if (i < nb) atomicAdd(&base_s[e], v); }
         }
@@ -401,6 +426,16 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     }
     disp_sync();
     if (tid == 0) trace_stamp(p, 8);
+    // the count of packet (me, e) is known: CTA (e mod G) tells the owner now.  Nothing precedes this word that the
+    // reader depends on (the rows are acknowledged through recv_rows), so a relaxed system-scope store is enough.
+    for (int e = (int)blockIdx.x + tid * G; e < E; e += DISP_THREADS * G) {
+        const int tot = total_s[e];
+        p.counts[e] = tot;
+        const int rows = tot < p.EC ? tot : p.EC;
+        const int owner = e / p.nLx, le = e - owner * p.nLx;
+        st_relaxed_sys_u64(p.peer_recv_flag[owner] + (size_t)p.rank * p.nLx + le,
+                           ((unsigned long long)p.epoch << 32) | (unsigned int)rows);
+    }
     // Row copies through the TMA engine: the chunk's token rows are contiguous in x, so one bulk load stages up to
     // 128 KiB of them in shared memory and every kept (token, pick) pair is one bulk store of a whole row into the
     // owner rank's receive buffer (peer-mapped over NVLink).  No per-lane load/store latency chains.
@@ -450,38 +485,28 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         }
     }
     bulk_wait_group0();        // this thread's row stores are complete ...
-    fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy flag traffic below
+    fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
     disp_sync();
     if (tid == 0) trace_stamp(p, 9);
-    if (tid == 0) {
-        fence_acq_rel_sys();  // this CTA's row stores (observed through the barrier) before the counter bump
-        const unsigned int old = atom_acq_rel_gpu_add_u32(p.disp_done, 1u);
-        misc[0] = (old == (unsigned int)G - 1u) ? 1u : 0u;
-        if (misc[0]) fence_acq_rel_sys();
-    }
-    disp_sync();
-    // the totals live in the pipeline stage area, which this CTA's own TMA producer may start filling as soon as the
-    // first flag below is visible: read them into registers first (E <= 1024 => at most 7 per thread)
-    int tot_r[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) tot_r[i] = (tid + i * DISP_THREADS < E) ? total_s[tid + i * DISP_THREADS] : 0;
-    disp_sync();
-    // from here this CTA's dispatch no longer touches the stage area: release the TMA producer (which entered its role
-    // right after the grid barrier and may already hold a tile of a REMOTE packet whose flag arrived early)
-    if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
-    if (misc[0]) {  // last CTA to finish: every chunk's rows are out; publish {epoch, rows} to the owners
-#pragma unroll
-        for (int i = 0; i < 7; ++i) {
-            const int e = tid + i * DISP_THREADS;
-            if (e >= E) break;
-            const int tot = tot_r[i];
-            p.counts[e] = tot;
-            const int rows = tot < p.EC ? tot : p.EC;
+    // acknowledge: this chunk's rows of expert e occupy slots [base, base + own) of packet (me, e), cut at EC.  The
+    // release covers every dispatch thread's completed row / record stores (observed through the barrier above).
+    const unsigned int par = p.epoch & 1u;
+    for (int e = tid; e < E; e += DISP_THREADS) {
+        const int lo = base_s[e];
+        const int hi = min(lo + own_s[e], p.EC);
+        if (hi > lo) {
             const int owner = e / p.nLx, le = e - owner * p.nLx;
-            st_release_sys_u64(p.peer_recv_flag[owner] + (size_t)p.rank * p.nLx + le,
-                               ((unsigned long long)p.epoch << 32) | (unsigned int)rows);
+            unsigned int* ctr = p.peer_recv_rows[owner] + ((size_t)par * p.num_pkts + (size_t)(p.rank * p.nLx + le)) * p.TCM;
+            for (int b = lo / BLOCK_M; b <= (hi - 1) / BLOCK_M; ++b) {
+                const int n = min(hi, (b + 1) * BLOCK_M) - max(lo, b * BLOCK_M);
+                red_release_sys_add_u32(ctr + b, (unsigned int)n);
+            }
         }
     }
+    disp_sync();
+    // from here this CTA's dispatch no longer touches the stage area: release the TMA producer (which entered its role
+    // right after the grid barrier and may already hold a tile whose rows arrived early)
+    if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
 }
 
 // ============================================================================================================
@@ -585,6 +610,15 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                         while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
                             g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, blk.pkt, mblk + r, 0);
                     }
+                } else if (p.phase_mask & 1u) {  // GEMM0 needs its row blocks of the packet to have landed (dispatch acks)
+                    for (int r = 0; r < mstep; ++r) {
+                        const int need = r == 0 ? rows0 : rows1;
+                        if (need == 0) break;
+                        SpinGuard g;
+                        const unsigned int* ctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + blk.pkt) * p.TCM + mblk + r;
+                        while (ld_acquire_sys_u32(ctr) < (unsigned int)need)
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, blk.pkt, mblk + r, need);
+                    }
                 }
                 ti.kind = blk.kind; ti.pkt = blk.pkt; ti.mblk = mblk; ti.ntile = nt;
                 ti.rows[0] = rows0; ti.rows[1] = rows1;
@@ -651,7 +685,6 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
             const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
             const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
             const int b_rows = ti.bn / PC::B_ROWS_DIV;
-            const uint32_t tx_cta = (uint32_t)(A_STAGE_BYTES + b_rows * BLOCK_K * 2);
             const int a_row = ti.a_row + (PAIR ? (int)crank * BLOCK_M : 0);
             const int b_row = ti.b_row + (PAIR ? (int)crank * b_rows : 0);
             const int take_at = min(ti.nk - 1, max(0, ti.nk - p.claim_ahead_kb));
@@ -670,19 +703,23 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
                 if (kb == take_at && crank == 0) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
                 uint8_t* sa = smem + stage * PC::STAGE_BYTES;
-                if (p.dbg_flags & 1) {   // experiment: no loads, barrier traffic only
-                    if (PAIR && crank != 0) mbar_arrive_cluster_plain(&full[stage], 0);
-                    else mbar_arrive(&full[stage]);
-                } else if (PAIR) {
-                    if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * tx_cta);
-                    else mbar_arrive_cluster_plain(&full[stage], 0);
+                const bool ld_a = (p.dbg_flags & 5) == 0, ld_b = (p.dbg_flags & 9) == 0;   // experiments only
+                const uint32_t tx = (ld_a ? (uint32_t)A_STAGE_BYTES : 0u) + (ld_b ? (uint32_t)(b_rows * BLOCK_K * 2) : 0u);
+                if (PAIR) {
+                    // the leader's expect_tx covers both CTAs' bytes (every completion is credited to ITS barrier), so
+                    // the partner's producer needs no arrival of its own: it only has to wait for its `empty` slot
+                    if (crank == 0) {
+                        if (tx) mbar_arrive_expect_tx(&full[stage], 2u * tx); else mbar_arrive(&full[stage]);
+                    } else if (p.dbg_flags & 16) {
+                        mbar_arrive_cluster_plain(&full[stage], 0);
+                    }
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[stage]), 0);
-                    tma_load_2d_pair(sa, ta, kb * BLOCK_K, a_row, leader_full);
-                    tma_load_2d_pair(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, leader_full);
+                    if (ld_a) tma_load_2d_pair(sa, ta, kb * BLOCK_K, a_row, leader_full);
+                    if (ld_b) tma_load_2d_pair(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, leader_full);
                 } else {
-                    mbar_arrive_expect_tx(&full[stage], tx_cta);
-                    tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
-                    tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
+                    if (tx) mbar_arrive_expect_tx(&full[stage], tx); else mbar_arrive(&full[stage]);
+                    if (ld_a) tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
+                    if (ld_b) tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
                 }
                 if (++stage == PC::STAGES) { stage = 0; phase ^= 1; }
             }
@@ -759,9 +796,10 @@ __device__ __noinline__ float gelu_erf(float v) {   // GELU, erf form (cutlass::
 enum : int { EPI_G0_RELU = 0, EPI_G0_GELU = 1, EPI_G1_STORE = 2, EPI_G1_FUSED_ADD = 3, EPI_G1_FUSED_COPY = 4 };
 
 struct DrainArgs {
-    uint8_t* stg;                  // this warp's 32 x 144 B transpose tile
+    uint8_t* stg;                  // this warp's 32 x 128 B transpose tile (16-byte pieces XOR-swizzled by row & 7)
     uint32_t t_row;                // TMEM address of this warp's lane quarter, accumulator column 0
-    int nchunks, lane, quarter, my_rows, N, n0;
+    int c0, c1;                    // this warp's 64-column chunks [c0, c1) of the tile
+    int lane, quarter, my_rows, N, n0;
     const __nv_bfloat16* bias;     // [N] or nullptr
     __nv_bfloat16* out_rows;       // row 0 of the destination row block (h staging or return buffer)
     __nv_bfloat16* acc_base;       // fused GEMM1: the source rank's output accumulator
@@ -777,12 +815,13 @@ struct DrainArgs {
 template <int MODE, bool HAS_BIAS, bool PAIR>
 __device__ __forceinline__ void drain_accumulator(const FmParams& p, const DrainArgs& a) {
     uint8_t* my_row = a.stg + a.lane * EPI_ROW_BYTES;
-    for (int c = 0; c < a.nchunks; ++c) {
+    const int sw = a.lane & 7;
+    for (int c = a.c0; c < a.c1; ++c) {
         uint32_t v[2][32];
         tmem_ld_32x32b_x32(a.t_row + c * 64, v[0]);
         tmem_ld_32x32b_x32(a.t_row + c * 64 + 32, v[1]);
         tmem_ld_wait();
-        if (c == a.nchunks - 1) {  // last TMEM read of this accumulator: hand it back to the MMA issuer
+        if (c == a.c1 - 1) {  // last TMEM read of this warp: hand its share of the accumulator back to the MMA issuer
             tcgen05_fence_before();
             __syncwarp();
             if (a.lane == 0) release_to_leader<PAIR>(a.release_bar, a.crank);
@@ -815,7 +854,7 @@ __device__ __forceinline__ void drain_accumulator(const FmParams& p, const Drain
                 uint4 o;
                 o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
                 o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-                *reinterpret_cast<uint4*>(my_row + (half * 4 + g) * 16) = o;
+                *reinterpret_cast<uint4*>(my_row + (((half * 4 + g) ^ sw) << 4)) = o;
             }
         }
         __syncwarp();
@@ -823,7 +862,7 @@ __device__ __forceinline__ void drain_accumulator(const FmParams& p, const Drain
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + (a.lane >> 3), seg = a.lane & 7;
-            const uint4 o = *reinterpret_cast<const uint4*>(a.stg + r * EPI_ROW_BYTES + seg * 16);
+            const uint4 o = *reinterpret_cast<const uint4*>(a.stg + r * EPI_ROW_BYTES + ((seg ^ (r & 7)) << 4));
             const int row_in_tile = a.quarter * 32 + r;
             if (MODE == EPI_G1_FUSED_ADD || MODE == EPI_G1_FUSED_COPY) {
                 // row -> its token's output row on the source rank (k == 1: plain copy, reference processor.cuh:170-203)
@@ -837,11 +876,14 @@ __device__ __forceinline__ void drain_accumulator(const FmParams& p, const Drain
             }
         }
         __syncwarp();
-        if (a.stamp && c == 0) trace_stamp(p, 121);
+        if (a.stamp && c == a.c0) trace_stamp(p, 121);
     }
 }
 
-// warps 4-7 of every CTA: TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced global / peer stores
+// warps 4-11 of every CTA: TMEM -> registers -> bias/activation -> bf16 -> smem transpose -> coalesced global / peer stores.
+// Warp w reads TMEM lanes [32*(w%4), +32) (a hardware restriction) and the column half (w-4)/4 of the tile.  The
+// release fence and the counter / flag traffic that make a finished tile visible to its consumers are NOT done here:
+// lane 0 of every epilogue warp arrives on pub_full[] and the publisher warp takes over (ffn_publisher).
 template <bool PAIR>
 __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t tmem_base,
                                              uint32_t crank) {
@@ -849,11 +891,14 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
     uint64_t* tmem_empty = bars + BAR_TMEM_EMPTY;
     uint64_t* sched_full = bars + BAR_SCHED_FULL;
     uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
+    uint64_t* pub_full = bars + BAR_PUB_FULL;
+    uint64_t* pub_empty = bars + BAR_PUB_EMPTY;
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) are the only ones this warp may read
-    uint8_t* stg = smem + OFF_EPI + quarter * EPI_WARP_BYTES;
-    int q = 0, qphase = 0, as = 0, aphase = 0, ntiles = 0;
+    const int chalf = (warp - EPI_WARP0) >> 2;
+    uint8_t* stg = smem + OFF_EPI + (warp - EPI_WARP0) * EPI_WARP_BYTES;
+    int q = 0, qphase = 0, as = 0, aphase = 0, ps = 0, pphase = 0, ntiles = 0;
     for (;;) {
         wait_sched_full<PAIR>(p, &sched_full[q], qphase, 100 + q);
         const TileInfo ti = ring[q];
@@ -876,7 +921,11 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             const int e_global = p.rank * p.nLx + ti.le;
             out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)my_mblk * BLOCK_M) * p.H;
         }
-        const int nchunks = my_rows > 0 ? min(ti.bn / 64, (N - n0) / 64) : 0;
+        // 64-column chunks of the tile that exist (N is a multiple of 64, not necessarily of the tile width), split
+        // between the two warps of this lane quarter
+        const int per_half = ti.bn / 128;
+        const int nvalid = my_rows > 0 ? min(ti.bn / 64, (N - n0) / 64) : 0;
+        const int c0 = min(chalf * per_half, nvalid), c1 = min(c0 + per_half, nvalid);
         // fused GEMM1 -> combine: this thread owns accumulator row (quarter*32 + lane); fetch that row's routing record
         const bool fuse = p.fused != 0 && ti.kind == 1;
         int my_tok = 0;
@@ -894,9 +943,9 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         const bool stamp_tile = (ntiles == 2) && tid == EPI_WARP0 * 32;
         if (stamp_tile) trace_stamp(p, 120);
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * BLOCK_N;
-        {
+        if (c1 > c0) {
             DrainArgs da;
-            da.stg = stg; da.t_row = t_row; da.nchunks = nchunks; da.lane = lane; da.quarter = quarter;
+            da.stg = stg; da.t_row = t_row; da.c0 = c0; da.c1 = c1; da.lane = lane; da.quarter = quarter;
             da.my_rows = my_rows; da.N = N; da.n0 = n0; da.bias = bias; da.out_rows = out_rows; da.acc_base = acc_base;
             da.my_tok = my_tok; da.my_pw = my_pw; da.my_mcw = my_mcw; da.release_bar = &tmem_empty[as]; da.crank = crank;
             da.stamp = stamp_tile;
@@ -920,48 +969,89 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
                     default: drain_accumulator<EPI_G1_FUSED_COPY, true, PAIR>(p, da); break;
                 }
             }
-        }
-        if (stamp_tile) trace_stamp(p, 122);
-        if (nchunks <= 0) {  // nothing to drain (row block past the packet's rows): still release the accumulator
+        } else {  // nothing to drain for this warp (row block or columns past the end): still release the accumulator
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) release_to_leader<PAIR>(&tmem_empty[as], crank);
         }
+        if (stamp_tile) trace_stamp(p, 122);
         if (++as == 2) { as = 0; aphase ^= 1; }
 
-        // publish: all 128 epilogue threads' stores -> one counter bump / flag
-        if (ti.kind == 0) fence_proxy_async_global();   // h will be read by TMA (async proxy) on other SMs
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (stamp_tile) trace_stamp(p, 123);
+        // hand the tile to the publisher: this warp's stores are issued (h will be read through the async proxy)
+        if (ti.kind == 0) fence_proxy_async_global();
+        __syncwarp();
+        if (lane == 0) {
+            mbar_wait(&pub_empty[ps], pphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_PUB, ps);
+            mbar_arrive(&pub_full[ps]);
+        }
+        if (++ps == 2) { ps = 0; pphase ^= 1; }
         if (tid == EPI_WARP0 * 32) {
             if (ntiles < 48) trace_stamp(p, 64 + ntiles);
-            if (my_rows > 0) {
-                if (ti.kind == 0) {
-                    fence_proxy_async_global();
-                    red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
-                } else if (fuse) {
-                    fence_acq_rel_sys();   // this tile's adds are performed before the packet counter moves
-                    const unsigned int old = atom_acq_rel_gpu_add_u32(p.pkt_done + ti.pkt, 1u);
-                    const unsigned int want = (unsigned int)(((ti.cnt + BLOCK_M - 1) / BLOCK_M) * p.TN1);
-                    if (old + 1u == want) {   // every GEMM1 tile of packet (src, le) has been added into src's output
-                        fence_acq_rel_sys();
-                        st_release_sys_u64(p.peer_done_flag[ti.src] + (size_t)(p.rank * p.nLx + ti.le),
-                                           (unsigned long long)p.epoch << 32);
-                    }
-                } else {
-                    fence_acq_rel_sys();
-                    const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
-                    if (old == (unsigned int)p.TN1 - 1u) {  // whole rows of this block are on the source rank
-                        fence_acq_rel_sys();
-                        const int e_global = p.rank * p.nLx + ti.le;
-                        st_release_sys_u64(p.peer_ret_flag[ti.src] + (size_t)e_global * p.TCM + my_mblk,
-                                           ((unsigned long long)p.epoch << 32) | (unsigned int)my_rows);
-                    }
-                }
-            }
-            if (ntiles == 2) trace_stamp(p, 124);
+            if (ntiles == 2) trace_stamp(p, 123);
         }
         ++ntiles;
+    }
+}
+
+// warp 2 of every CTA: makes finished tiles visible.  For every tile of the ring, once all epilogue warps of this CTA
+// have issued their stores: GEMM0 -> release-add on the row block's h counter (reference notifyNext's tSA counter,
+// processor.cuh:490-615); GEMM1 -> system-scope fence, then the packet / row-block counter and, from the last tile, the
+// flag on the source rank (reference processor.cuh:722-750).  The fences wait for the stores / REDs to drain (1-2 us,
+// more over NVLink); here they overlap the next tile's epilogue instead of delaying it.
+template <bool PAIR>
+__device__ __forceinline__ void ffn_publisher(const FmParams& p, uint8_t* smem, uint64_t* bars, uint32_t crank) {
+    uint64_t* sched_full = bars + BAR_SCHED_FULL;
+    uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
+    uint64_t* pub_full = bars + BAR_PUB_FULL;
+    uint64_t* pub_empty = bars + BAR_PUB_EMPTY;
+    const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
+    const int lane = threadIdx.x & 31;
+    int q = 0, qphase = 0, ps = 0, pphase = 0, ntiles = 0;
+    for (;;) {
+        int kind = -1;
+        if (lane == 0) {
+            wait_sched_full<PAIR>(p, &sched_full[q], qphase, 400 + q);
+            const TileInfo ti = ring[q];
+            release_to_leader<PAIR>(&sched_empty[q], crank);
+            kind = ti.kind;
+            if (kind >= 0) {
+                const int my_rows = ti.rows[PAIR ? crank : 0];
+                const int my_mblk = ti.mblk + (PAIR ? (int)crank : 0);
+                mbar_wait(&pub_full[ps], pphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_PUB, 10 + ps);
+                mbar_arrive(&pub_empty[ps]);
+                if (my_rows > 0) {
+                    if (kind == 0) {
+                        fence_proxy_async_global();
+                        red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                    } else if (p.fused) {
+                        fence_acq_rel_sys();   // this tile's adds are performed before the packet counter moves
+                        const unsigned int old = atom_acq_rel_gpu_add_u32(p.pkt_done + ti.pkt, 1u);
+                        const unsigned int want = (unsigned int)(((ti.cnt + BLOCK_M - 1) / BLOCK_M) * p.TN1);
+                        if (old + 1u == want) {   // every GEMM1 tile of packet (src, le) has been added into src's output
+                            fence_acq_rel_sys();
+                            st_release_sys_u64(p.peer_done_flag[ti.src] + (size_t)(p.rank * p.nLx + ti.le),
+                                               (unsigned long long)p.epoch << 32);
+                        }
+                    } else {
+                        fence_acq_rel_sys();
+                        const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                        if (old == (unsigned int)p.TN1 - 1u) {  // whole rows of this block are on the source rank
+                            fence_acq_rel_sys();
+                            const int e_global = p.rank * p.nLx + ti.le;
+                            st_release_sys_u64(p.peer_ret_flag[ti.src] + (size_t)e_global * p.TCM + my_mblk,
+                                               ((unsigned long long)p.epoch << 32) | (unsigned int)my_rows);
+                        }
+                    }
+                }
+                if (ntiles == 2) trace_stamp(p, 124);
+            }
+        }
+        kind = __shfl_sync(0xffffffffu, kind, 0);
+        if (++q == NSCHED) { q = 0; qphase ^= 1; }
+        if (++ps == 2) { ps = 0; pphase ^= 1; }
+        ++ntiles;
+        if (kind < 0) break;
+        __syncwarp();
     }
 }
 
@@ -972,14 +1062,20 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + OFF_TMEM_PTR);
     const int tid = threadIdx.x, warp = tid >> 5;
     if (warp == 1 && (tid & 31) == 0) {
-        // arrival counts: full = leader's expect_tx (+ the peer producer's arrive); empty / tmem_full = one tcgen05.commit;
-        // tmem_empty = one lane per epilogue warp (of both CTAs); sched_empty = producer(s) + MMA lane + epilogue warps
+        // arrival counts: full = leader's expect_tx; empty / tmem_full = one tcgen05.commit; tmem_empty = one lane per
+        // epilogue warp (of both CTAs); pub_full = one lane per epilogue warp of this CTA; sched_empty = every ring reader
         const int nc = PAIR ? 2 : 1;
-        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[BAR_FULL + i], nc); mbar_init(&bars[BAR_EMPTY + i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars[BAR_TMEM_FULL + i], 1); mbar_init(&bars[BAR_TMEM_EMPTY + i], 4 * nc); }
+        const int nfull = (PAIR && (p.dbg_flags & 16)) ? 2 : 1;
+        for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[BAR_FULL + i], nfull); mbar_init(&bars[BAR_EMPTY + i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[BAR_TMEM_FULL + i], 1);
+            mbar_init(&bars[BAR_TMEM_EMPTY + i], NUM_EPI_WARPS * nc);
+            mbar_init(&bars[BAR_PUB_FULL + i], NUM_EPI_WARPS);
+            mbar_init(&bars[BAR_PUB_EMPTY + i], 1);
+        }
         for (int i = 0; i < NSCHED; ++i) {
             mbar_init(&bars[BAR_SCHED_FULL + i], 1);
-            mbar_init(&bars[BAR_SCHED_EMPTY + i], 1 + 5 * nc);
+            mbar_init(&bars[BAR_SCHED_EMPTY + i], 1 + (2 + NUM_EPI_WARPS) * nc);   // MMA lane + per CTA: producer, publisher, epilogue warps
             mbar_init(&bars[BAR_PROD_TAKE + i], 1);
         }
         mbar_init(&bars[BAR_XROWS], 1);
@@ -1003,6 +1099,7 @@ __device__ __forceinline__ void ffn_roles(const FmParams& p, uint8_t* smem, uint
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
     if (warp == 0) ffn_producer<PAIR>(p, smem, bars, crank);
     else if (warp == 1) { if (crank == 0) ffn_mma<PAIR>(p, smem, bars, tmem_base); }
+    else if (warp == 2) ffn_publisher<PAIR>(p, smem, bars, crank);
     else if (warp == 3) { if (crank == 0) ffn_scheduler<PAIR>(p, smem, bars); }
     else if (warp >= EPI_WARP0) ffn_epilogue<PAIR>(p, smem, bars, tmem_base, crank);
 }
@@ -1184,10 +1281,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
                 p.g1_done[i] = 0u;
             }
             for (int i = tid; i < p.num_pkts; i += NUM_THREADS) p.pkt_done[i] = 0u;
-            if (tid == 0) {
-                *p.claim = 0u;
-                *p.disp_done = 0u;
-            }
+            // the arrival counters of the NEXT epoch's parity: nobody reads them any more (launch epoch-1 is over) and no
+            // peer can write them yet (a rank starts forward epoch+1 only after this launch has returned all its rows)
+            unsigned int* next_rows = p.recv_rows + (size_t)((p.epoch + 1u) & 1u) * p.num_pkts * p.TCM;
+            for (int i = tid; i < p.num_pkts * p.TCM; i += NUM_THREADS) next_rows[i] = 0u;
+            if (tid == 0) *p.claim = 0u;
         }
         gate_phase(p, smem, t0, n_tok);
         if (tid == 0) trace_stamp(p, 1);

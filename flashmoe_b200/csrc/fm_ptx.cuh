@@ -34,6 +34,8 @@ enum : unsigned int {
     FM_TRAP_RECV_FLAG = 8,
     FM_TRAP_G0_DONE = 9,
     FM_TRAP_RET_FLAG = 10,
+    FM_TRAP_RECV_ROWS = 11,
+    FM_TRAP_MBAR_PUB = 12,
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -130,6 +132,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
 }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_sys_add_u32(unsigned int* p, unsigned int v) {  // also on peer-mapped addresses
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
     unsigned int v;

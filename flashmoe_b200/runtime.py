@@ -216,7 +216,7 @@ class MoEContext:
         npk = d["world"] * d["num_local_experts"]
         shapes = {"topk_idx": (S, k), "topk_w": (S, k), "mcw": (S,), "slot": (S, k), "counts": (E,),
                   "recv_x": (npk, d["pEC"], H), "hidden": (npk, d["pEC"], P), "ret_y": (E, d["pEC"], H),
-                  "gate_out": (S, E), "recv_cnt": (npk,), "trace": (d["num_sms"], 128)}
+                  "gate_out": (S, E), "recv_cnt": (npk,), "trace": (d["grid"], 128)}
         return arr.reshape(shapes[name])
 
     @property

@@ -72,6 +72,7 @@ typedef struct fm_dims {
     int32_t k, EC, pEC, TCM;
     int32_t world, rank, num_local_experts;
     int32_t num_sms, smem_bytes;
+    int32_t grid; /* CTAs of the persistent kernel (= num_sms, rounded down to even for CTA pairs); rows of FM_BUF_TRACE */
 } fm_dims_t;
 
 typedef struct fm_ctx fm_ctx_t;
@@ -136,7 +137,7 @@ enum fm_buffer {
     FM_BUF_RET_Y = 7,    /* bf16  [E, pEC, H]       expert outputs returned to this rank */
     FM_BUF_GATE_OUT = 8, /* bf16  [S, E]  full softmax row (reference gateOut[S,PX] without the padding columns) */
     FM_BUF_RECV_CNT = 9, /* int32 [W, nLx] rows received per (source rank, local expert) in the last forward */
-    FM_BUF_TRACE = 10    /* u64   [num_sms, 128] %globaltimer stamps of the last forward (fm_set_trace) */
+    FM_BUF_TRACE = 10    /* u64   [grid, 128] %globaltimer stamps of the last forward (fm_set_trace) */
 };
 FM_API int fm_buffer_bytes(const fm_ctx_t* ctx, int which, size_t* bytes);
 FM_API int fm_read_buffer(fm_ctx_t* ctx, int which, void* host_dst, size_t bytes);

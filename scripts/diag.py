@@ -72,7 +72,8 @@ def stage(args):
         print(f"  dispatch rows checked {tot}, wrong {bad}")
     if st in ("ffn", "combine"):
         ctx.forward(xd, wgd, wed, phase_mask=2); ctx.synchronize()
-        rx = ctx.read("recv_x"); hid = ctx.read("hidden"); ry = ctx.read("ret_y"); rc = ctx.read("recv_cnt")
+        rx = ctx.read("recv_x"); hid = ctx.read("hidden"); rc = ctx.read("recv_cnt")
+        ry = ctx.read("ret_y")  # needs FM_FUSED_COMBINE=0 (the fused path has no return buffer)
         print("  recv_cnt", rc.tolist())
         for e in range(E):
             n = int(min(counts[e], EC))

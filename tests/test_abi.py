@@ -48,7 +48,7 @@ def test_compiled_config_is_the_json(lib):
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.FmConfig) == 15 * 4 and ctypes.sizeof(_lib.FmDims) == 15 * 4
+    assert ctypes.sizeof(_lib.FmConfig) == 15 * 4 and ctypes.sizeof(_lib.FmDims) == 16 * 4
     text = open(HEADER).read()
     cfg_fields = re.findall(r"int32_t\s+(\w+);", text.split("typedef struct fm_config")[1].split("} fm_config_t")[0])
     assert cfg_fields == [f for f, _ in _lib.FmConfig._fields_]
