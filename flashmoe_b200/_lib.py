@@ -13,6 +13,7 @@ from . import config as _config
 LIB_PATH = Path(__file__).resolve().parent / "libflashmoe_b200.so"
 FM_MAX_WORLD = 16
 FM_IPC_HANDLE_BYTES = 64
+FM_HOST_SLOTS = 3
 
 # enum fm_buffer
 BUF_TOPK_IDX, BUF_TOPK_W, BUF_MCW, BUF_SLOT, BUF_COUNTS, BUF_RECV_X, BUF_HIDDEN, BUF_RET_Y, BUF_GATE_OUT, BUF_RECV_CNT, BUF_TRACE = range(11)
@@ -21,7 +22,7 @@ BUF_TOPK_IDX, BUF_TOPK_W, BUF_MCW, BUF_SLOT, BUF_COUNTS, BUF_RECV_X, BUF_HIDDEN,
 EXPORTED_SYMBOLS = (
     "fm_compiled_config", "fm_create", "fm_destroy", "fm_get_dims", "fm_num_local_experts", "fm_symm_size",
     "fm_symm_local_ptr", "fm_symm_export", "fm_symm_attach_ipc", "fm_symm_attach_ptrs", "fm_symm_use_external",
-    "fm_moe_forward", "fm_moe_forward_host", "fm_check", "fm_set_timeout_ms", "fm_set_trace", "fm_launch_count",
+    "fm_moe_forward", "fm_moe_forward_host", "fm_host_submit", "fm_host_wait", "fm_check", "fm_set_timeout_ms", "fm_set_trace", "fm_launch_count",
     "fm_buffer_bytes",
     "fm_read_buffer", "fm_debug_forward", "fm_last_error", "fm_version",
 )
@@ -73,6 +74,8 @@ def load() -> ctypes.CDLL:
     L.fm_symm_use_external.argtypes = [vp, vp, ctypes.c_size_t]
     L.fm_moe_forward.argtypes = [vp, cvp, cvp, cvp, cvp, cvp, vp, vp]
     L.fm_moe_forward_host.argtypes = [vp, cvp, cvp, cvp, cvp, cvp, vp, vp]
+    L.fm_host_submit.argtypes = [vp, cvp, cvp, cvp, cvp, cvp, vp, vp, ctypes.POINTER(ctypes.c_uint64)]
+    L.fm_host_wait.argtypes = [vp, ctypes.c_uint64]
     L.fm_debug_forward.argtypes = [vp, cvp, cvp, cvp, cvp, cvp, vp, vp, ctypes.c_uint32]
     L.fm_check.argtypes = [vp]
     L.fm_set_timeout_ms.argtypes = [vp, ctypes.c_uint32]

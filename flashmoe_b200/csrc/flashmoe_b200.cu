@@ -127,8 +127,14 @@ struct fm_ctx {
     int* recv_cnt = nullptr;
     fm::TileBlock* blocks = nullptr;
     __nv_bfloat16* hidden = nullptr;
-    __nv_bfloat16* x_stage = nullptr;    // host-path staging
-    __nv_bfloat16* out_stage = nullptr;
+    // host-buffer path (fm_host_submit / fm_host_wait): FM_HOST_SLOTS staging pairs, three streams, so the H2D copy of
+    // step i+1 and the D2H copy of step i-1 run under the kernel of step i (PCIe is full duplex; steps are independent)
+    __nv_bfloat16* x_stage[FM_HOST_SLOTS] = {};
+    __nv_bfloat16* out_stage[FM_HOST_SLOTS] = {};
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[FM_HOST_SLOTS] = {}, ev_kernel[FM_HOST_SLOTS] = {}, ev_d2h[FM_HOST_SLOTS] = {};
+    bool host_ready = false;
+    uint64_t host_submitted = 0, host_waited = 0;
     // symmetric slab
     void* symm = nullptr;
     bool symm_external = false;
@@ -582,10 +588,18 @@ FM_API int fm_destroy(fm_ctx_t* ctx) {
     for (int r = 0; r < ctx->d.world; ++r)
         if (ctx->peer_opened[r] && ctx->peer_base[r] != nullptr) cudaIpcCloseMemHandle(ctx->peer_base[r]);
     void* bufs[] = {ctx->topk_idx, ctx->topk_w, ctx->mcw, ctx->slot, ctx->counts, ctx->gate_out, ctx->chunk_counts,
-                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->pkt_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace, ctx->x_stage,
-                    ctx->out_stage};
+                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->pkt_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace};
     for (void* b : bufs)
         if (b != nullptr) cudaFree(b);
+    for (int i = 0; i < FM_HOST_SLOTS; ++i) {
+        if (ctx->x_stage[i] != nullptr) cudaFree(ctx->x_stage[i]);
+        if (ctx->out_stage[i] != nullptr) cudaFree(ctx->out_stage[i]);
+        if (ctx->ev_h2d[i] != nullptr) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_kernel[i] != nullptr) cudaEventDestroy(ctx->ev_kernel[i]);
+        if (ctx->ev_d2h[i] != nullptr) cudaEventDestroy(ctx->ev_d2h[i]);
+    }
+    if (ctx->s_h2d != nullptr) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h != nullptr) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->symm != nullptr && !ctx->symm_external) cudaFree(ctx->symm);
     if (ctx->dbg_host != nullptr) cudaFreeHost(ctx->dbg_host);
     delete ctx;
@@ -681,22 +695,74 @@ FM_API int fm_debug_forward(fm_ctx_t* ctx, const void* x, const void* gate_w, co
     return launch(ctx, x, gate_w, expert_w, bias_up, bias_down, out, static_cast<cudaStream_t>(stream), phase_mask);
 }
 
+// ---- host-buffer entry points -----------------------------------------------------------------------------------
+static int host_setup(fm_ctx* c) {
+    if (c->host_ready) return FM_OK;
+    const size_t elems = (size_t)c->d.S * c->d.H;
+    int rc;
+    for (int i = 0; i < FM_HOST_SLOTS; ++i) {
+        if ((rc = dev_alloc(&c->x_stage[i], elems, false))) return rc;
+        if ((rc = dev_alloc(&c->out_stage[i], elems, false))) return rc;
+        FM_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        FM_CUDA(cudaEventCreateWithFlags(&c->ev_kernel[i], cudaEventDisableTiming));
+        FM_CUDA(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
+    }
+    FM_CUDA(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    FM_CUDA(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    c->host_ready = true;
+    return FM_OK;
+}
+
+FM_API int fm_host_submit(fm_ctx_t* ctx, const void* x_host, const void* gate_w, const void* expert_w, const void* bias_up,
+                          const void* bias_down, void* out_host, void* stream, uint64_t* ticket) {
+    if (ctx == nullptr || x_host == nullptr || out_host == nullptr || ticket == nullptr) return fail(FM_EINVAL, "null argument");
+    FM_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = host_setup(ctx))) return rc;
+    if (ctx->host_submitted - ctx->host_waited >= FM_HOST_SLOTS)
+        return fail(FM_ESTATE, "%d steps in flight: call fm_host_wait on the oldest ticket first", FM_HOST_SLOTS);
+    const size_t bytes = (size_t)ctx->d.S * ctx->d.H * 2;
+    const int slot = (int)(ctx->host_submitted % FM_HOST_SLOTS);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // x_stage[slot] was last read by the kernel of step (submitted - SLOTS): the H2D copy waits for that kernel
+    // (out_stage[slot]'s previous D2H has been waited for on the host already, see the in-flight bound above)
+    if (ctx->host_submitted >= FM_HOST_SLOTS) FM_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_kernel[slot], 0));
+    FM_CUDA(cudaMemcpyAsync(ctx->x_stage[slot], x_host, bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    FM_CUDA(cudaEventRecord(ctx->ev_h2d[slot], ctx->s_h2d));
+    FM_CUDA(cudaStreamWaitEvent(s, ctx->ev_h2d[slot], 0));
+    if ((rc = launch(ctx, ctx->x_stage[slot], gate_w, expert_w, bias_up, bias_down, ctx->out_stage[slot], s, 7u))) return rc;
+    FM_CUDA(cudaEventRecord(ctx->ev_kernel[slot], s));
+    FM_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_kernel[slot], 0));
+    FM_CUDA(cudaMemcpyAsync(out_host, ctx->out_stage[slot], bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    FM_CUDA(cudaEventRecord(ctx->ev_d2h[slot], ctx->s_d2h));
+    *ticket = ctx->host_submitted++;
+    return FM_OK;
+}
+
+FM_API int fm_host_wait(fm_ctx_t* ctx, uint64_t ticket) {
+    if (ctx == nullptr) return fail(FM_EINVAL, "null context");
+    if (ticket >= ctx->host_submitted) return fail(FM_EINVAL, "ticket %llu was never issued", (unsigned long long)ticket);
+    if (ticket < ctx->host_waited) return FM_OK;   // already complete
+    if (ticket != ctx->host_waited) return fail(FM_ESTATE, "tickets must be waited for in submission order (oldest is %llu)",
+                                                (unsigned long long)ctx->host_waited);
+    FM_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaEventSynchronize(ctx->ev_d2h[ticket % FM_HOST_SLOTS]);
+    int rc;
+    if ((rc = check_kernel_status(ctx))) return rc;
+    if (e != cudaSuccess) return fail(FM_ECUDA, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+    ctx->host_waited = ticket + 1;
+    return FM_OK;
+}
+
 FM_API int fm_moe_forward_host(fm_ctx_t* ctx, const void* x_host, const void* gate_w, const void* expert_w,
                                const void* bias_up, const void* bias_down, void* out_host, void* stream) {
-    if (ctx == nullptr || x_host == nullptr || out_host == nullptr) return fail(FM_EINVAL, "null argument");
-    FM_CUDA(cudaSetDevice(ctx->device));
-    const size_t bytes = (size_t)ctx->d.S * ctx->d.H * 2;
+    if (ctx == nullptr) return fail(FM_EINVAL, "null context");
     int rc;
-    if (ctx->x_stage == nullptr && (rc = dev_alloc(&ctx->x_stage, bytes / 2, false))) return rc;
-    if (ctx->out_stage == nullptr && (rc = dev_alloc(&ctx->out_stage, bytes / 2, false))) return rc;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    FM_CUDA(cudaMemcpyAsync(ctx->x_stage, x_host, bytes, cudaMemcpyHostToDevice, s));
-    if ((rc = launch(ctx, ctx->x_stage, gate_w, expert_w, bias_up, bias_down, ctx->out_stage, s, 7u))) return rc;
-    FM_CUDA(cudaMemcpyAsync(out_host, ctx->out_stage, bytes, cudaMemcpyDeviceToHost, s));
-    cudaError_t e = cudaStreamSynchronize(s);
-    if ((rc = check_kernel_status(ctx))) return rc;
-    if (e != cudaSuccess) return fail(FM_ECUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
-    return FM_OK;
+    while (ctx->host_waited < ctx->host_submitted)   // drain earlier asynchronous steps first
+        if ((rc = fm_host_wait(ctx, ctx->host_waited))) return rc;
+    uint64_t t = 0;
+    if ((rc = fm_host_submit(ctx, x_host, gate_w, expert_w, bias_up, bias_down, out_host, stream, &t))) return rc;
+    return fm_host_wait(ctx, t);
 }
 
 FM_API int fm_check(fm_ctx_t* ctx) {

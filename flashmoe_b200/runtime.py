@@ -70,6 +70,9 @@ def _check_tensor(name: str, t: torch.Tensor, device: torch.device) -> None:
         raise RuntimeError(f"{name} must be contiguous")
     if t.dtype != torch.bfloat16:
         raise RuntimeError(f"{name} must be torch.bfloat16 (compiled Element), got {t.dtype}")
+    if t.data_ptr() % 16:
+        raise RuntimeError(f"{name} must start on a 16-byte boundary (TMA tensor maps, bulk row copies and the vector "
+                           f"accesses need it); got storage offset {t.storage_offset()}")
 
 
 class MoEContext:
@@ -114,19 +117,10 @@ class MoEContext:
     def num_local_experts(self) -> int:
         return self.dims["num_local_experts"]
 
-    def _validate(self, input: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor) -> None:
-        """Same conditions as the reference's TORCH_CHECKs (python_bindings.cu:22-65) plus a dtype check."""
+    def _validate_weights(self, gate_weights: torch.Tensor, expert_weights: torch.Tensor) -> None:
         d = self.dims
-        _check_tensor("Input", input, self.device)
         _check_tensor("Gate weights", gate_weights, self.device)
         _check_tensor("Expert weights", expert_weights, self.device)
-        if input.dim() != 3:
-            raise RuntimeError("Input must be 3D [batch, seq, H]")
-        if input.size(0) * input.size(1) != d["S"]:
-            raise RuntimeError(f"Input batch*seq must equal compiled S={d['S']}. Got batch={input.size(0)}, "
-                               f"seq={input.size(1)} (product={input.size(0) * input.size(1)})")
-        if input.size(2) != d["H"]:
-            raise RuntimeError(f"Input hidden_size must equal compiled H={d['H']}. Got {input.size(2)}")
         if gate_weights.dim() != 2 or gate_weights.size(0) != d["H"] or gate_weights.size(1) != d["E"]:
             raise RuntimeError(f"Gate weights must be [H={d['H']}, E={d['E']}]. Got {list(gate_weights.shape)}")
         nlx = d["num_local_experts"]
@@ -137,6 +131,19 @@ class MoEContext:
         if expert_weights.size(2) != d["P"] or expert_weights.size(3) != d["H"]:
             raise RuntimeError(f"Expert weights must be [*, 2, P={d['P']}, H={d['H']}]. Got [*, 2, "
                                f"{expert_weights.size(2)}, {expert_weights.size(3)}]")
+
+    def _validate(self, input: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor) -> None:
+        """Same conditions as the reference's TORCH_CHECKs (python_bindings.cu:22-65) plus dtype and alignment checks."""
+        d = self.dims
+        _check_tensor("Input", input, self.device)
+        if input.dim() != 3:
+            raise RuntimeError("Input must be 3D [batch, seq, H]")
+        if input.size(0) * input.size(1) != d["S"]:
+            raise RuntimeError(f"Input batch*seq must equal compiled S={d['S']}. Got batch={input.size(0)}, "
+                               f"seq={input.size(1)} (product={input.size(0) * input.size(1)})")
+        if input.size(2) != d["H"]:
+            raise RuntimeError(f"Input hidden_size must equal compiled H={d['H']}. Got {input.size(2)}")
+        self._validate_weights(gate_weights, expert_weights)
 
     def _bias_ptrs(self, bias_up, bias_down):
         d = self.dims
@@ -171,25 +178,48 @@ class MoEContext:
         _lib.check(rc)
         return out
 
-    def forward_host(self, input_host: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor,
-                     out_host: Optional[torch.Tensor] = None, bias_up: Optional[torch.Tensor] = None,
-                     bias_down: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """End-to-end call with HOST activations (pinned for full PCIe rate): H2D copy, fused forward, D2H copy,
-        stream synchronise.  Weights stay device-resident (they are parameters, not per-step inputs)."""
+    def _host_args(self, input_host, gate_weights, expert_weights, out_host, bias_up, bias_down):
         d = self.dims
-        if input_host.is_cuda or input_host.dtype != torch.bfloat16 or not input_host.is_contiguous():
-            raise RuntimeError("input_host must be a contiguous CPU torch.bfloat16 tensor")
-        if input_host.numel() != d["S"] * d["H"]:
-            raise RuntimeError(f"input_host must hold S*H = {d['S'] * d['H']} elements")
-        _check_tensor("Gate weights", gate_weights, self.device)
-        _check_tensor("Expert weights", expert_weights, self.device)
+        for name, t in (("input_host", input_host), ("out_host", out_host)):
+            if t is None:
+                continue
+            if t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous():
+                raise RuntimeError(f"{name} must be a contiguous CPU torch.bfloat16 tensor")
+            if t.numel() != d["S"] * d["H"]:
+                raise RuntimeError(f"{name} must hold S*H = {d['S'] * d['H']} elements")
+        self._validate_weights(gate_weights, expert_weights)
         bu, bd = self._bias_ptrs(bias_up, bias_down)
         if out_host is None:
             out_host = torch.empty_like(input_host, pin_memory=True)
+        return out_host, bu, bd
+
+    def forward_host(self, input_host: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor,
+                     out_host: Optional[torch.Tensor] = None, bias_up: Optional[torch.Tensor] = None,
+                     bias_down: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """End-to-end call with HOST activations (pinned for full PCIe rate): H2D copy, fused forward, D2H copy, wait.
+        Weights stay device-resident (they are parameters, not per-step inputs).  Blocking; for throughput use
+        submit_host / wait_host, which keep up to three steps in flight so the copies overlap the kernels."""
+        out_host, bu, bd = self._host_args(input_host, gate_weights, expert_weights, out_host, bias_up, bias_down)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._L.fm_moe_forward_host(self._ctx, input_host.data_ptr(), gate_weights.data_ptr(),
                                                expert_weights.data_ptr(), bu, bd, out_host.data_ptr(), stream))
         return out_host
+
+    def submit_host(self, input_host: torch.Tensor, gate_weights: torch.Tensor, expert_weights: torch.Tensor,
+                    out_host: torch.Tensor, bias_up: Optional[torch.Tensor] = None,
+                    bias_down: Optional[torch.Tensor] = None) -> int:
+        """Asynchronous host-buffer step: enqueue H2D copy -> layer -> D2H copy and return a ticket at once
+        (at most `_lib.FM_HOST_SLOTS` tickets outstanding).  `out_host` is complete after `wait_host(ticket)`."""
+        out_host, bu, bd = self._host_args(input_host, gate_weights, expert_weights, out_host, bias_up, bias_down)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ticket = ctypes.c_uint64()
+        _lib.check(self._L.fm_host_submit(self._ctx, input_host.data_ptr(), gate_weights.data_ptr(),
+                                          expert_weights.data_ptr(), bu, bd, out_host.data_ptr(), stream,
+                                          ctypes.byref(ticket)))
+        return int(ticket.value)
+
+    def wait_host(self, ticket: int) -> None:
+        _lib.check(self._L.fm_host_wait(self._ctx, int(ticket)))
 
     def set_trace(self, enable: bool) -> None:
         _lib.check(self._L.fm_set_trace(self._ctx, 1 if enable else 0))

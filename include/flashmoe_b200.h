@@ -114,9 +114,20 @@ FM_API int fm_moe_forward(fm_ctx_t* ctx, const void* x, const void* gate_w, cons
                           const void* bias_up, const void* bias_down, void* out, void* stream);
 
 /* Same, with the activations in HOST memory (pinned for full PCIe speed): copies x host->device, runs the layer,
- * copies out device->host on `stream`, then synchronises the stream (the reference's blocking behaviour). */
+ * copies out device->host, then waits for the result (the reference's blocking behaviour,
+ * python_bindings.cu:131-148).  Equivalent to fm_host_submit + fm_host_wait. */
 FM_API int fm_moe_forward_host(fm_ctx_t* ctx, const void* x_host, const void* gate_w, const void* expert_w,
                                const void* bias_up, const void* bias_down, void* out_host, void* stream);
+
+/* Pipelined form of the host-buffer call: fm_host_submit enqueues H2D copy -> layer -> D2H copy for one step and
+ * returns a ticket at once; up to FM_HOST_SLOTS steps may be in flight, so the copies of neighbouring steps overlap
+ * the kernel (separate copy streams, PCIe full duplex).  The kernel runs on `stream`; weights must be ready there.
+ * fm_host_wait blocks until that step's out_host is complete; tickets are waited for in submission order.
+ * x_host must stay valid until its H2D copy has run (i.e. until the step's ticket has been waited for). */
+#define FM_HOST_SLOTS 3
+FM_API int fm_host_submit(fm_ctx_t* ctx, const void* x_host, const void* gate_w, const void* expert_w,
+                          const void* bias_up, const void* bias_down, void* out_host, void* stream, uint64_t* ticket);
+FM_API int fm_host_wait(fm_ctx_t* ctx, uint64_t ticket);
 
 /* Check the kernel's host-mapped status record after a synchronise; FM_EKERNEL + message if a wait timed out. */
 FM_API int fm_check(fm_ctx_t* ctx);

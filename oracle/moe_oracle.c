@@ -385,3 +385,81 @@ done:
     if (!abs_sum_out) free(abs_sum);
     return rc;
 }
+
+/* ------------------------------------------------------------------ whole layer on a SAMPLE of one rank's tokens
+ * Gate (A.2-A.4) and slots (A.5) run over all S tokens -- capacity drops depend on every earlier token -- but the
+ * expert FFN (A.6) and the combine (A.7) only for the n_sample tokens listed in `sample` (ascending or not).  The
+ * cost of the FFN is per row, so full-size shapes (d_model 4096, ffn 14336) stay at seconds.  out_sample [n_sample,H].
+ * Used by bench.py's post-run parity check and the full-size multi-GPU parity runs.
+ */
+FMO_API int fmo_forward_sample(const uint16_t* x, const uint16_t* wg_eff, const uint16_t* w_up,
+                               const uint16_t* w_down_eff, const uint16_t* b_up, const uint16_t* b_down, int S, int H,
+                               int P, int E, int k, int EC, int act, const int32_t* sample, int n_sample,
+                               uint16_t* out_sample, int32_t* topk_idx_out, int32_t* slot_out, int32_t* kept_out,
+                               int32_t* counts_out, float* mcw_out, uint16_t* gate_out_out, float* logits_out,
+                               float* abs_sum_out) {
+    const size_t SE = (size_t)S * E;
+    float* probs = (float*)malloc(sizeof(float) * SE);
+    int rc = -2;
+    uint16_t *rows = NULL, *hbuf = NULL, *ybuf = NULL;
+    int64_t *yoff = NULL, *fill = NULL, *rowpos = NULL;
+    if (!probs) goto done;
+    rc = fmo_gate(x, wg_eff, S, H, E, k, logits_out, probs, gate_out_out, topk_idx_out, mcw_out, abs_sum_out);
+    if (rc) goto done;
+    rc = fmo_slots(topk_idx_out, S, E, k, EC, slot_out, kept_out, counts_out);
+    if (rc) goto done;
+    rc = -2;
+    yoff = (int64_t*)calloc((size_t)E + 1, sizeof(int64_t));
+    fill = (int64_t*)calloc((size_t)E + 1, sizeof(int64_t));
+    rowpos = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n_sample ? n_sample : 1) * k);
+    if (!yoff || !fill || !rowpos) goto done;
+    for (int i = 0; i < n_sample; ++i) {
+        const int t = sample[i];
+        if (t < 0 || t >= S) { rc = -1; goto done; }
+        for (int j = 0; j < k; ++j)
+            if (kept_out[(size_t)t * k + j]) yoff[topk_idx_out[(size_t)t * k + j] + 1] += 1;
+    }
+    for (int e = 0; e < E; ++e) yoff[e + 1] += yoff[e];
+    {
+        const int64_t R = yoff[E];
+        rows = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)(R ? R : 1) * H);
+        hbuf = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)(R ? R : 1) * P);
+        ybuf = (uint16_t*)malloc(sizeof(uint16_t) * (size_t)(R ? R : 1) * H);
+        if (!rows || !hbuf || !ybuf) goto done;
+        for (int i = 0; i < n_sample; ++i) {
+            const int t = sample[i];
+            for (int j = 0; j < k; ++j) {
+                rowpos[(size_t)i * k + j] = -1;
+                if (kept_out[(size_t)t * k + j]) {
+                    const int e = topk_idx_out[(size_t)t * k + j];
+                    const int64_t r = yoff[e] + fill[e]++;
+                    rowpos[(size_t)i * k + j] = r;
+                    memcpy(rows + (size_t)r * H, x + (size_t)t * H, sizeof(uint16_t) * (size_t)H);
+                }
+            }
+        }
+        for (int e = 0; e < E; ++e) {
+            const int64_t r = yoff[e + 1] - yoff[e];
+            rc = fmo_expert_ffn(rows + (size_t)yoff[e] * H, r, H, P, w_up + (size_t)e * P * H,
+                                w_down_eff + (size_t)e * H * P, b_up ? b_up + (size_t)e * P : NULL,
+                                b_down ? b_down + (size_t)e * H : NULL, act, hbuf + (size_t)yoff[e] * P,
+                                ybuf + (size_t)yoff[e] * H);
+            if (rc) goto done;
+        }
+    }
+    for (int i = 0; i < n_sample; ++i) {
+        const int t = sample[i];
+        const uint16_t* yr[16];
+        uint16_t pt[16];
+        for (int j = 0; j < k; ++j) {
+            const int e = topk_idx_out[(size_t)t * k + j];
+            yr[j] = rowpos[(size_t)i * k + j] >= 0 ? ybuf + (size_t)rowpos[(size_t)i * k + j] * H : NULL;
+            pt[j] = gate_out_out[(size_t)t * E + e];
+        }
+        fmo_combine_token(yr, pt, mcw_out[t], k, H, out_sample + (size_t)i * H);
+    }
+    rc = 0;
+done:
+    free(rows); free(hbuf); free(ybuf); free(yoff); free(fill); free(rowpos); free(probs);
+    return rc;
+}

@@ -43,6 +43,7 @@ def lib() -> ctypes.CDLL:
         L.fmo_slots.restype = ctypes.c_int
         L.fmo_expert_ffn.restype = ctypes.c_int
         L.fmo_forward.restype = ctypes.c_int
+        L.fmo_forward_sample.restype = ctypes.c_int
         L.fmo_num_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -169,6 +170,39 @@ def forward(x: np.ndarray, wg_eff: np.ndarray, w_up: np.ndarray, w_down_eff: np.
         _p(mcw, _f32p), _p(gate_out, _u16p), _p(logits, _f32p), _p(abs_sum, _f32p))
     if rc != 0:
         raise RuntimeError(f"fmo_forward failed with code {rc}")
+    return OracleResult(out, topk, slot, kept, counts, mcw, gate_out, logits, ambiguity_flags(logits, abs_sum, k))
+
+
+def forward_sample(x: np.ndarray, wg_eff: np.ndarray, w_up: np.ndarray, w_down_eff: np.ndarray, sample: np.ndarray, *,
+                   k: int, EC: int, act: int = 0, b_up: Optional[np.ndarray] = None,
+                   b_down: Optional[np.ndarray] = None) -> OracleResult:
+    """Like `forward`, but the expert FFN + combine run only for the tokens listed in `sample` (routing, slots and
+    capacity drops are still computed over all S tokens).  `out` of the result is [len(sample), H] in sample order;
+    every other field covers all S tokens.  Keeps full-size shapes (d_model 4096, ffn 14336) at seconds of CPU."""
+    S, H = x.shape
+    E, P, H2 = w_up.shape
+    assert H2 == H and wg_eff.shape == (E, H) and w_down_eff.shape == (E, H, P)
+    sample = np.ascontiguousarray(sample, dtype=np.int32)
+    n = int(sample.size)
+    out = np.zeros((n, H), dtype=np.uint16)
+    topk = np.zeros((S, k), dtype=np.int32)
+    slot = np.zeros((S, k), dtype=np.int32)
+    kept = np.zeros((S, k), dtype=np.int32)
+    counts = np.zeros((E,), dtype=np.int32)
+    mcw = np.zeros((S,), dtype=np.float32)
+    gate_out = np.zeros((S, E), dtype=np.uint16)
+    logits = np.zeros((S, E), dtype=np.float32)
+    abs_sum = np.zeros((S,), dtype=np.float32)
+    rc = lib().fmo_forward_sample(
+        _p(np.ascontiguousarray(x), _u16p), _p(np.ascontiguousarray(wg_eff), _u16p),
+        _p(np.ascontiguousarray(w_up), _u16p), _p(np.ascontiguousarray(w_down_eff), _u16p),
+        _p(None if b_up is None else np.ascontiguousarray(b_up), _u16p),
+        _p(None if b_down is None else np.ascontiguousarray(b_down), _u16p),
+        ctypes.c_int(S), ctypes.c_int(H), ctypes.c_int(P), ctypes.c_int(E), ctypes.c_int(k), ctypes.c_int(EC),
+        ctypes.c_int(act), _p(sample, _i32p), ctypes.c_int(n), _p(out, _u16p), _p(topk, _i32p), _p(slot, _i32p),
+        _p(kept, _i32p), _p(counts, _i32p), _p(mcw, _f32p), _p(gate_out, _u16p), _p(logits, _f32p), _p(abs_sum, _f32p))
+    if rc != 0:
+        raise RuntimeError(f"fmo_forward_sample failed with code {rc}")
     return OracleResult(out, topk, slot, kept, counts, mcw, gate_out, logits, ambiguity_flags(logits, abs_sum, k))
 
 
