@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- MoE-layer forward tokens/s on B200 (BASELINE.json metric), one fused persistent kernel per step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME] [--sweeps a,b,..]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-Workload: BASELINE.json configs[1] (8 experts, top-2, S=4096 tokens per rank, d_model 1024, ffn 4096, bf16,
-capacity_factor 1, drop_tokens 1, ReLU, zero bias), synthetic N(0,1) activations/weights seeded per rank like the
-reference harness (flashmoe/worker.py:56-58); at N > 1 the 8 experts are sharded over the N ranks and every rank keeps
-its own 4096 tokens (weak scaling, per-GPU FLOPs fixed).
+Workload (default `--config B`): BASELINE.json configs[1] (8 experts, top-2, S=4096 tokens per rank, d_model 1024, ffn 4096,
+bf16, capacity_factor 1, drop_tokens 1, ReLU, zero bias), synthetic N(0,1) activations/weights seeded per rank like the
+reference harness (flashmoe/worker.py:56-58); at N > 1 the experts are sharded over the N ranks and every rank keeps its
+own S tokens (weak scaling, per-GPU FLOPs fixed).  `--config C | D1k | D4k | D16k | D64k | E8 .. E128` selects the other
+BASELINE.json shapes (flashmoe_b200/config.py); `--sweeps` appends reduced-step measurements of further configs to the
+same JSON line (`"sweeps": [...]`).
 
 Prints ONE JSON line (rank 0).  `value` = N*S / (max over ranks of the device time per step), inputs resident in HBM;
-`e2e` = the same metric through the public host-buffer entry point (pinned host activations in, host output back, copies
-inside the timed region).  `roofline` describes the dominant work (the two expert GEMMs on tcgen05) against the measured
-cuBLAS bf16 throughput of this pool (MEASURED_PEAKS.json); `cpu_baseline` is a plain torch CPU forward of the same
-layer on the host cores (a reported baseline, not a target).  `--impl reference` times that CPU implementation as the
-reference arm: the reference itself has no CPU path and cannot be built here, so the oracle port is
-the stated stand-in.
+`e2e` = the same metric through the public host-buffer entry point (pinned host activations in, host output back, every
+step's copies inside the timed region; steps are pipelined three deep so the copies overlap the kernels).  `roofline`
+describes the dominant work (the two expert GEMMs on tcgen05) against the measured cuBLAS bf16 throughput of this pool
+(MEASURED_PEAKS.json: burst peak when the timed region is shorter than a second, else sustained; both fractions are
+printed); `parity_check` is one extra forward on seeded, scaled inputs after the timed loops, every rank's output and
+top-k checked against the CPU oracle on a sample of its tokens (outside any timed region; a failure exits non-zero);
+`cpu_baseline` is a plain torch CPU forward of the same layer on the host cores (a reported baseline, not a target).
+`--impl reference` times that CPU implementation as the reference arm: the reference itself has no CPU path and cannot
+be built here, so the oracle port is the stated stand-in.
 """
 from __future__ import annotations
 
@@ -32,14 +37,32 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from flashmoe_b200.config import BASELINE_CONFIGS  # noqa: E402
 
-CFG = BASELINE_CONFIGS["B"]
-WORKLOAD = "configs[1]: 8 experts top-2 seq=4096 d_model=1024 ffn=4096 bf16 (per rank); experts sharded E/N"
+def _configs():
+    # flashmoe_b200.config is pure Python; imported by file path so that the reference arm never runs the package's
+    # __init__ (which maps the product's native library into the process)
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_fm_config", os.path.join(ROOT, "flashmoe_b200", "config.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_fm_config"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_CFG = _configs()
+BASELINE_CONFIGS, CONFIG_DESCRIPTIONS = _CFG.BASELINE_CONFIGS, _CFG.CONFIG_DESCRIPTIONS
 
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
+
+
+def config_dict(name, cfg, world):
+    """The `config` object of the JSON line; identical in both arms (the driver compares them)."""
+    return {"workload": CONFIG_DESCRIPTIONS[name], "name": name, "experts": cfg.E, "top_k": cfg.k, "tokens_per_rank": cfg.S,
+            "d_model": cfg.H, "ffn": cfg.P, "capacity_factor": cfg.capacity_factor, "drop_tokens": cfg.drop_tokens,
+            "hidden_act": "relu", "parallelism": f"ep{world}"}
 
 
 def make_inputs(cfg, nlx, rank):
@@ -49,7 +72,9 @@ def make_inputs(cfg, nlx, rank):
     gw = torch.Generator().manual_seed(0x5EED)
     x = torch.randn(cfg.mini_batch, cfg.sequence_len, cfg.H, generator=g).bfloat16()
     wg = torch.randn(cfg.H, cfg.E, generator=gw).bfloat16()
-    we = torch.randn(nlx, 2, cfg.P, cfg.H, generator=g).bfloat16()
+    we = torch.empty(nlx, 2, cfg.P, cfg.H, dtype=torch.bfloat16)
+    for i in range(nlx):  # per expert: keeps the fp32 temporary small at ffn 14336
+        we[i] = torch.randn(2, cfg.P, cfg.H, generator=g).bfloat16()
     return x, wg, we
 
 
@@ -64,10 +89,14 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons through NVML from a host thread while the timed region runs."""
+    """Samples SM clock / power / throttle reasons through NVML from a host thread while the timed regions run."""
+
+    REASONS = ("SwPowerCap", "HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "HwPowerBrakeSlowdown",
+               "ApplicationsClocksSetting")
+    NAMES = ("sw_power_cap", "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "hw_power_brake", "app_clocks")
 
     def __init__(self, index: int):
-        self.samples, self.stop_flag, self.thread, self.ok = [], False, None, False
+        self.samples, self.stop_flag, self.thread, self.ok, self.errors = [], False, None, False, 0
         try:
             import pynvml
 
@@ -79,15 +108,32 @@ class ClockSampler:
         except Exception:
             self.max_mhz = None
 
-    def _loop(self):
+    def _reasons(self):
         nv = self.nv
-        while not self.stop_flag:
+        for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
             try:
-                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
-                                     nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+                return int(getattr(nv, fn)(self.h))
             except Exception:
-                pass
-            time.sleep(0.002)
+                continue
+        return None
+
+    def sample_once(self):
+        nv = self.nv
+        try:
+            mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.errors += 1
+            return
+        try:
+            watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            watts = None
+        self.samples.append((time.perf_counter(), mhz, self._reasons(), watts))
+
+    def _loop(self):
+        while not self.stop_flag:
+            self.sample_once()
+            time.sleep(0.001)
 
     def start(self):
         if self.ok:
@@ -99,22 +145,31 @@ class ClockSampler:
         if self.thread is not None:
             self.thread.join(timeout=1.0)
 
-    def summary(self, t0, t1):
+    def summary(self, windows):
+        """`windows`: list of (t0, t1) host-time intervals during which the GPU was running timed work."""
         if not self.ok:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"]}
-        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"], "samples": 0}
+        inside = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
         mhz = sorted(s[1] for s in inside)
-        nv = self.nv
-        names = {"sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap, "hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
-                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
-                 "hw_power_brake": nv.nvmlClocksEventReasonHwPowerBrakeSlowdown,
-                 "app_clocks": nv.nvmlClocksEventReasonApplicationsClocksSetting}
-        bits = 0
+        nv, bits, known = self.nv, 0, False
         for s in inside:
-            bits |= s[2]
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(n for n, b in names.items() if bits & b), "samples": len(inside)}
+            if s[2] is not None:
+                bits |= s[2]
+                known = True
+        reasons = []
+        for attr, name in zip(self.REASONS, self.NAMES):
+            for prefix in ("nvmlClocksEventReason", "nvmlClocksThrottleReason"):
+                b = getattr(nv, prefix + attr, None)
+                if b is not None:
+                    if bits & b:
+                        reasons.append(name)
+                    break
+        if not known:
+            reasons.append("reasons_unavailable")
+        watts = [s[3] for s in inside if s[3] is not None]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_mhz_min": mhz[0] if mhz else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(inside), "power_w_max": max(watts) if watts else None,
+                "sampler_errors": self.errors}
 
 
 def usable_cpus() -> int:
@@ -130,39 +185,39 @@ def usable_cpus() -> int:
     return max(1, n)
 
 
-def cpu_forward_tokens_per_s(cfg, budget_s, steps_hint=3):
-    """Prepare the plain torch CPU MoE forward (oracle/torch_moe.py) of the bench workload on the host cores: runs one
-    full-size warm-up forward to size a bounded per-step sample.  Returns (torch_moe module, x sample [tokens,H], gate
-    weights, expert weights, config of the sample, tokens per step, seconds of the full-size warm-up)."""
+def cpu_forward_sample(cfg, budget_s, steps_hint=3):
+    """Prepare the plain torch CPU MoE forward (oracle/torch_moe.py) of the bench workload on the host cores: one
+    warm-up forward on a probe of the workload sizes a bounded per-step sample (about `budget_s` seconds in total).
+    Returns (torch_moe module, x sample [tokens,H], gate weights, expert weights, EC of the sample, tokens per step)."""
     from oracle import torch_moe
 
     torch.set_num_threads(usable_cpus())
     x, wg, we = make_inputs(cfg, cfg.E, 0)
     S = cfg.S
     xs = x.reshape(S, cfg.H)
+    probe = min(S, 512)
+    ec_of = lambda n: cfg.replace(sequence_len=n, mini_batch=1).EC  # noqa: E731
     t0 = time.perf_counter()
-    torch_moe.moe_forward_cpu(xs, wg, we, k=cfg.k, EC=cfg.EC, act=cfg.hidden_act)  # warm-up, also sizes the sample
-    t_full = time.perf_counter() - t0
-    tokens = S
-    if t_full * (steps_hint + 1) > budget_s:  # bound the sample: fewer tokens per step, capacity scaled with them
-        tokens = max(128, int(S * budget_s / (t_full * (steps_hint + 1))) // 128 * 128)
-    sub = cfg.replace(sequence_len=tokens, mini_batch=1)
-    xsub = xs[:tokens].contiguous()
-    return torch_moe, xsub, wg, we, sub, tokens, t_full
+    torch_moe.moe_forward_cpu(xs[:probe].contiguous(), wg, we, k=cfg.k, EC=ec_of(probe), act=cfg.hidden_act)
+    t_probe = time.perf_counter() - t0
+    per_tok = t_probe / probe
+    tokens = int(budget_s / ((steps_hint + 1) * per_tok)) // 128 * 128
+    tokens = max(128, min(S, tokens))
+    return torch_moe, xs[:tokens].contiguous(), wg, we, ec_of(tokens), tokens
 
 
 def run_reference_arm(args, rank, world):
     """The reference arm: the CPU implementation of the path (oracle port: plain torch CPU MoE forward), all host threads."""
     if rank != 0:
         return 0
-    cfg = CFG
-    budget = float(os.environ.get("FM_BENCH_CPU_BUDGET_S", "150"))
-    torch_moe, xsub, wg, we, sub, tokens, t_full = cpu_forward_tokens_per_s(cfg, budget, steps_hint=args.steps + args.warmup)
-    for _ in range(max(0, args.warmup - 1)):
-        torch_moe.moe_forward_cpu(xsub, wg, we, k=cfg.k, EC=sub.EC, act=cfg.hidden_act)
+    cfg = BASELINE_CONFIGS[args.config]
+    budget = float(os.environ.get("FM_BENCH_CPU_BUDGET_S", "120"))
+    torch_moe, xsub, wg, we, ec, tokens = cpu_forward_sample(cfg, budget, steps_hint=args.steps + args.warmup)
+    for _ in range(max(0, args.warmup)):
+        torch_moe.moe_forward_cpu(xsub, wg, we, k=cfg.k, EC=ec, act=cfg.hidden_act)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        torch_moe.moe_forward_cpu(xsub, wg, we, k=cfg.k, EC=sub.EC, act=cfg.hidden_act)
+        torch_moe.moe_forward_cpu(xsub, wg, we, k=cfg.k, EC=ec, act=cfg.hidden_act)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     tps = tokens / dt
     cores = torch.get_num_threads()
@@ -170,13 +225,201 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": "moe_layer_fwd_tokens_per_s", "value": tps, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "reference has no CPU path and cannot be built here; this is the oracle "
-                       "port (oracle/torch_moe.py) on the host cores"},
+            "config": config_dict(args.config, cfg, args.gpus),
+            "note": "the reference has no CPU path and cannot be built here; this arm is the oracle port "
+                    "(oracle/torch_moe.py) on the host cores",
             "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class Env:
+    def __init__(self, rank, world, dev):
+        self.rank, self.world, self.dev = rank, world, dev
+
+    def barrier(self):
+        import torch.distributed as dist
+
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, v):
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, v):
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device=self.dev)
+        dist.all_reduce(t)
+        return int(t.item())
+
+
+def parity_check(env, ctx, cfg, xd, wgd, wed, n_tokens):
+    """One extra forward on SCALED weights (non-degenerate softmax, O(1) activations), every rank's output and top-k
+    indices against the CPU oracle on a seeded sample of its tokens.  All experts' weights are all-gathered (the oracle's
+    world composition); the oracle's cost is per sampled token, so full-size shapes stay cheap."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from oracle import moe_oracle as mo
+
+    scale = cfg.H ** -0.5
+    wgd.mul_(scale)
+    wed.mul_(scale)
+    out = ctx.forward(xd, wgd, wed)
+    ctx.synchronize()
+    topk = ctx.read("topk_idx")
+    if env.world > 1:
+        wes = [torch.empty_like(wed) for _ in range(env.world)]
+        dist.all_gather(wes, wed)
+        full = torch.cat([w.cpu() for w in wes], dim=0)
+        del wes
+    else:
+        full = wed.cpu()
+    up, down = mo.split_expert_weights(mo.to_bits(full))
+    del full
+    rng = np.random.default_rng(1234 + env.rank)
+    sample = np.sort(rng.choice(cfg.S, size=min(n_tokens, cfg.S), replace=False)).astype(np.int32)
+    xb = mo.to_bits(xd.cpu().reshape(cfg.S, cfg.H))
+    ref = mo.forward_sample(xb, mo.gate_weights_effective(mo.to_bits(wgd.cpu()), cfg.E, cfg.H), up, down, sample,
+                            k=cfg.k, EC=cfg.EC, act=cfg.hidden_act)
+    mism = (topk != ref.topk_idx).any(axis=1)
+    hard = int((mism & ~ref.ambiguous).sum())
+    got = mo.bits_to_f32(mo.to_bits(out.cpu().reshape(cfg.S, cfg.H))[sample]).astype(np.float64)
+    want = mo.bits_to_f32(ref.out).astype(np.float64)
+    ok_rows = ~mism[sample]
+    finite = bool(np.isfinite(got).all())
+    relf = float(np.linalg.norm(got[ok_rows] - want[ok_rows]) / max(np.linalg.norm(want[ok_rows]), 1e-30)) if finite else float("inf")
+    ok = finite and hard == 0 and relf <= 1e-3
+    res = torch.tensor([relf if finite else 1e30, float(hard), float(int(mism.sum())), 0.0 if ok else 1.0],
+                       dtype=torch.float64, device=env.dev)
+    if env.world > 1:
+        allr = [torch.empty_like(res) for _ in range(env.world)]
+        dist.all_gather(allr, res)
+        allr = torch.stack(allr).cpu()
+    else:
+        allr = res.cpu().unsqueeze(0)
+    return {"n_ranks": env.world, "tokens_checked": int(len(sample)) * env.world, "tokens_routed_per_rank": cfg.S,
+            "relF_max": float(allr[:, 0].max()), "topk_mismatch_unambiguous": int(allr[:, 1].sum()),
+            "topk_mismatch_ambiguous": int(allr[:, 2].sum() - allr[:, 1].sum()), "tolerance_relF": 1e-3,
+            "inputs": "x N(0,1), gate/expert weights N(0,1)*d_model^-0.5, seeded; checked against oracle/moe_oracle.c",
+            "ok": bool(allr[:, 3].sum() == 0)}
+
+
+def run_config(env, name, steps, warmup, sampler, *, e2e=True, parity_tokens=0, out_in_slab=True):
+    """Measure one configuration; returns a dict with the device-resident and end-to-end numbers."""
+    from flashmoe_b200.runtime import MoEContext
+
+    rank, world, dev = env.rank, env.world, env.dev
+    cfg = BASELINE_CONFIGS[name]
+    nlx = cfg.num_local_experts(world)
+    ctx = MoEContext(cfg, rank=rank, world=world, device=dev.index, timeout_ms=30000)
+    x, wg, we = make_inputs(cfg, nlx, rank)
+    xd, wgd, wed = x.to(dev), wg.to(dev), we.to(dev)
+    del we
+    # at N > 1 peers add their expert outputs into this rank's symmetric accumulator; asking for the output THERE
+    # (ctx.output_buffer()) saves the final copy into a caller tensor.  N == 1 accumulates straight into `out`.
+    out = ctx.output_buffer() if (out_in_slab and world > 1) else torch.empty_like(xd)
+
+    for _ in range(warmup):
+        ctx.forward(xd, wgd, wed, out=out)
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count
+    t_host0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        ctx.forward(xd, wgd, wed, out=out)
+    e1.record()
+    env.barrier()
+    t_host1 = time.perf_counter()
+    ctx.check()
+    launches = ctx.launch_count - launches0
+    ms = env.max_over_ranks(e0.elapsed_time(e1) / steps)
+    windows = [(t_host0, t_host1)]
+    rows_exec = int(ctx.read("recv_cnt").sum())  # token-expert pairs this rank's experts executed (after drops)
+    rows_total = env.sum_over_ranks(rows_exec)
+    res = {"name": name, "ms": ms, "launches": launches, "rows_total": rows_total, "cfg": cfg, "nlx": nlx,
+           "out_buffer": "symmetric accumulator (MoEContext.output_buffer)" if (out_in_slab and world > 1) else "caller tensor"}
+
+    if e2e:
+        # end-to-end arm: host activations in, host output back, EVERY step; three steps in flight (public API:
+        # MoEContext.submit_host / wait_host -> fm_host_submit / fm_host_wait), so copies overlap kernels
+        depth = 3
+        x_pins = [x.clone().pin_memory() for _ in range(depth)]
+        out_pins = [torch.empty_like(x).pin_memory() for _ in range(depth)]
+        e2e_steps = max(6, min(steps, 60))
+
+        def run_e2e(n):
+            tickets = []
+            for i in range(n):
+                if len(tickets) == depth:
+                    ctx.wait_host(tickets.pop(0))
+                tickets.append(ctx.submit_host(x_pins[i % depth], wgd, wed, out_pins[i % depth]))
+            for t in tickets:
+                ctx.wait_host(t)
+
+        run_e2e(depth + 2)
+        env.barrier()
+        t0 = time.perf_counter()
+        run_e2e(e2e_steps)
+        t1 = time.perf_counter()
+        env.barrier()
+        res["e2e_ms"] = env.max_over_ranks((t1 - t0) / e2e_steps * 1e3)
+        windows.append((t0, t1))
+        # the blocking single call (H2D -> kernel -> D2H -> wait), for context
+        ctx.forward_host(x_pins[0], wgd, wed, out_pins[0])
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.forward_host(x_pins[0], wgd, wed, out_pins[0])
+        res["e2e_blocking_ms"] = env.max_over_ranks((time.perf_counter() - t0) / 5 * 1e3)
+        res["e2e_steps"], res["e2e_depth"] = e2e_steps, depth
+        del x_pins, out_pins
+    res["clocks"] = sampler.summary(windows)
+    if parity_tokens > 0:
+        res["parity"] = parity_check(env, ctx, cfg, xd, wgd, wed, parity_tokens)
+    env.barrier()
+    ctx.close()
+    del xd, wgd, wed, out
+    torch.cuda.empty_cache()
+    env.barrier()
+    return res
+
+
+def derived(res, world, peaks, steps):
+    """Roofline figures of one measured configuration."""
+    cfg, ms, rows_total, nlx = res["cfg"], res["ms"], res["rows_total"], res["nlx"]
+    S, H, P, E = cfg.S, cfg.H, cfg.P, cfg.E
+    flops_rank = 4.0 * (rows_total / world) * H * P + 2.0 * S * H * E  # 4*R*H*P + 2*S*H*E per rank
+    achieved = flops_rank / (ms * 1e-3) / 1e12
+    timed_s = steps * ms * 1e-3
+    kind = "burst" if timed_s < 1.0 else "sustained"
+    peak = peaks["bf16_burst"] if kind == "burst" else peaks["bf16_sustained"]
+    hbm_alg = S * H * 2 * 2 + E * H * 2 + nlx * 2 * H * P * 2 + (rows_total / world) * (2 * H + 2 * P) * 2
+    nvl_bytes = 2.0 * (rows_total / world) * (1.0 - 1.0 / world) * H * 2  # per GPU per direction: rows out + outputs back
+    nvl_floor_ms = nvl_bytes / 770e9 * 1e3   # measured peer-copy bandwidth of this pool (B200_PROFILING.md)
+    flop_floor_ms = flops_rank / (peak * 1e12) * 1e3
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_kind": f"{kind} cuBLAS bf16 ({'timed region %.3f s' % timed_s}), {peaks['source']}",
+            "frac_of_burst": achieved / peaks["bf16_burst"], "frac_of_sustained": achieved / peaks["bf16_sustained"],
+            "algorithmic_flops_per_launch": flops_rank, "algorithmic_hbm_bytes_per_launch": hbm_alg,
+            "hbm_frac_of_measured_copy": hbm_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+            "nvlink_bytes_per_dir_per_gpu": nvl_bytes, "nvlink_floor_ms_at_770GBs": nvl_floor_ms,
+            "flop_floor_ms": flop_floor_ms, "frac_of_slower_floor": max(nvl_floor_ms, flop_floor_ms) / ms}
 
 
 def main():
@@ -185,7 +428,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="B", choices=sorted(BASELINE_CONFIGS))
+    ap.add_argument("--sweeps", default=os.environ.get("FM_BENCH_SWEEPS", ""),
+                    help="comma-separated extra configs measured with reduced steps and appended as \"sweeps\"")
+    ap.add_argument("--sweep-steps", type=int, default=20)
+    ap.add_argument("--parity-tokens", type=int, default=int(os.environ.get("FM_BENCH_PARITY_TOKENS", "256")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world != args.gpus:
@@ -198,8 +447,6 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
-    from flashmoe_b200.runtime import MoEContext
-
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the MoE forward path has no CPU fallback", file=sys.stderr)
         return 3
@@ -209,122 +456,93 @@ def main():
 
     if world > 1:
         dist.init_process_group(backend="cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=dev)
-    cfg = CFG
-    nlx = cfg.num_local_experts(world)
-    ctx = MoEContext(cfg, rank=rank, world=world, device=dev.index, timeout_ms=20000)
-    x, wg, we = make_inputs(cfg, nlx, rank)
-    x_pin, out_pin = x.pin_memory(), torch.empty_like(x).pin_memory()
-    xd, wgd, wed = x.to(dev), wg.to(dev), we.to(dev)
-    out = torch.empty_like(xd)
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    env = Env(rank, world, dev)
+    peaks = load_peaks()
     sampler = ClockSampler(dev.index)
     sampler.start()
-    # ---- device-resident arm: W warm-up + K timed launches between two CUDA events on the launching stream ----
-    for _ in range(args.warmup):
-        ctx.forward(xd, wgd, wed, out=out)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = ctx.launch_count
-    t_host0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        ctx.forward(xd, wgd, wed, out=out)
-    e1.record()
-    barrier()
-    t_host1 = time.perf_counter()
-    ctx.check()
-    launches = ctx.launch_count - launches0
-    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    clocks = sampler.summary(t_host0, t_host1)
-    rows_exec = int(ctx.read("recv_cnt").sum())  # token-expert pairs this rank's experts executed (after drops)
 
-    # ---- end-to-end arm: host activations in, host output back, every step ----
-    e2e_steps = max(3, min(args.steps, 50))
-    for _ in range(3):
-        ctx.forward_host(x_pin, wgd, wed, out_pin)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        ctx.forward_host(x_pin, wgd, wed, out_pin)  # synchronises the stream before returning
-    barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) / e2e_steps * 1e3)
-    sampler.stop()
-
-    S, H, P, E, k = cfg.S, cfg.H, cfg.P, cfg.E, cfg.k
-    if world > 1:
-        t = torch.tensor([rows_exec], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)
-        rows_total = int(t.item())
-    else:
-        rows_total = rows_exec
-    peaks = load_peaks()
-    flops_rank = 4.0 * (rows_total / world) * H * P + 2.0 * S * H * E  # SURVEY.md 8(d): 4*R*H*P + 2*S*H*E per rank
-    achieved = flops_rank / (ms * 1e-3) / 1e12
-    traffic = None
+    name = args.config
+    cfg = BASELINE_CONFIGS[name]
+    res = run_config(env, name, args.steps, args.warmup, sampler, e2e=not args.no_e2e, parity_tokens=args.parity_tokens)
+    S, ms = cfg.S, res["ms"]
+    roof = derived(res, world, peaks, args.steps)
+    # DRAM traffic per launch comes from a committed `ncu --set full` capture; it describes one configuration at one N only
+    roof["traffic"] = None
     prof = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            if pj.get("config", "B") == name and int(pj.get("n_gpus", 1)) == world:
+                roof["traffic"] = pj.get("dram_bytes_per_launch")
+                roof["traffic_source"] = pj.get("source")
         except Exception:
-            traffic = None
-    hbm_alg = S * H * 2 * 2 + E * H * 2 + nlx * 2 * H * P * 2 + (rows_total / world) * (2 * H + 2 * P) * 2
-    # per-GPU NVLink bytes per direction: dispatch rows out + expert outputs back, remote fraction 1 - 1/W
-    nvl_bytes = 2.0 * (rows_total / world) * (1.0 - 1.0 / world) * H * 2
-    nvl_floor_ms = nvl_bytes / 770e9 * 1e3   # measured peer-copy bandwidth of this pool (B200_PROFILING.md)
-    flop_floor_ms = flops_rank / (peaks["bf16_sustained"] * 1e12) * 1e3
+            pass
+    cd = config_dict(name, cfg, world)
     line = {
         "metric": "moe_layer_fwd_tokens_per_s", "value": world * S / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "experts": E, "top_k": k, "tokens_per_rank": S, "d_model": H, "ffn": P,
-                   "capacity_factor": cfg.capacity_factor, "drop_tokens": cfg.drop_tokens, "hidden_act": "relu",
-                   "parallelism": f"ep{world}", "token_expert_pairs_executed": rows_total,
-                   "l2": "no explicit flush: per-step working set (weights 134 MB + activations/staging 118 MB per rank) "
-                         "exceeds the 126 MB L2"},
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_sustained"], "traffic": traffic,
-                     "peak_kind": "sustained cuBLAS bf16, " + peaks["source"],
-                     "algorithmic_flops_per_launch": flops_rank, "algorithmic_hbm_bytes_per_launch": hbm_alg,
-                     "hbm_frac_of_measured_copy": hbm_alg / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                     "nvlink_bytes_per_dir_per_gpu": nvl_bytes, "nvlink_floor_ms_at_770GBs": nvl_floor_ms,
-                     "flop_floor_ms": flop_floor_ms,
-                     "frac_of_slower_floor": max(nvl_floor_ms, flop_floor_ms) / ms},
-        "e2e": {"value": world * S / (e2e_ms * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": S * H * 2,
-                "d2h_bytes_per_step": S * H * 2, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                "api": "MoEContext.forward_host -> fm_moe_forward_host (pinned host activations, device-resident weights)"},
-        "gpu_launches": launches, "clocks": clocks,
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cd,
+        "run": {"token_expert_pairs_executed": res["rows_total"], "output_buffer": res["out_buffer"],
+                "l2": "no explicit flush: the per-step working set (expert weights + activations/staging, >= 250 MB per "
+                      "rank for config B) exceeds the 126 MB L2"},
+        "roofline": roof, "gpu_launches": res["launches"], "clocks": res["clocks"],
     }
+    if "e2e_ms" in res:
+        line["e2e"] = {"value": world * S / (res["e2e_ms"] * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": S * cfg.H * 2,
+                       "d2h_bytes_per_step": S * cfg.H * 2, "ms_per_step": res["e2e_ms"], "steps": res["e2e_steps"],
+                       "pipeline_depth": res["e2e_depth"], "blocking_call_ms": res["e2e_blocking_ms"],
+                       "api": "MoEContext.submit_host/wait_host -> fm_host_submit/fm_host_wait (pinned host activations in, "
+                              "pinned host output back every step, device-resident weights; copies overlap kernels)"}
+    if "parity" in res:
+        line["parity_check"] = res["parity"]
+
+    sweeps = [s for s in args.sweeps.split(",") if s]
+    if sweeps:
+        line["sweeps"] = []
+        t_budget = time.perf_counter() + float(os.environ.get("FM_BENCH_SWEEP_BUDGET_S", "240"))
+        for sname in sweeps:
+            if sname not in BASELINE_CONFIGS or BASELINE_CONFIGS[sname].E % world:
+                line["sweeps"].append({"config": sname, "skipped": "num_experts not divisible by the world size"})
+                continue
+            if time.perf_counter() > t_budget:
+                line["sweeps"].append({"config": sname, "skipped": "sweep time budget exhausted"})
+                continue
+            try:
+                r = run_config(env, sname, args.sweep_steps, max(3, args.sweep_steps // 4), sampler, e2e=False,
+                               parity_tokens=int(os.environ.get("FM_BENCH_SWEEP_PARITY_TOKENS", "0")))
+                rf = derived(r, world, peaks, args.sweep_steps)
+                c = r["cfg"]
+                entry = {"config": sname, "workload": CONFIG_DESCRIPTIONS[sname], "tokens_per_s": world * c.S / (r["ms"] * 1e-3),
+                         "ms_per_step": r["ms"], "steps": args.sweep_steps, "tflops_per_gpu": rf["achieved"],
+                         "frac_of_burst": rf["frac_of_burst"], "frac_of_sustained": rf["frac_of_sustained"],
+                         "nvlink_floor_ms_at_770GBs": rf["nvlink_floor_ms_at_770GBs"], "flop_floor_ms_burst": rf["algorithmic_flops_per_launch"] / (peaks["bf16_burst"] * 1e12) * 1e3,
+                         "token_expert_pairs_executed": r["rows_total"], "clocks": r["clocks"]}
+                if "parity" in r:
+                    entry["parity_check"] = r["parity"]
+                line["sweeps"].append(entry)
+            except Exception as exc:  # keep the headline line even if a sweep point fails
+                line["sweeps"].append({"config": sname, "error": str(exc)[:300]})
+                break
+    sampler.stop()
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         budget = float(os.environ.get("FM_BENCH_CPU_BUDGET_S", "20"))
-        torch_moe, xsub, wg_c, we_c, sub, tokens, t_full = cpu_forward_tokens_per_s(cfg, budget)
+        torch_moe, xsub, wg_c, we_c, ec, tokens = cpu_forward_sample(cfg, budget)
         iters = 3
         t0 = time.perf_counter()
         for _ in range(iters):
-            torch_moe.moe_forward_cpu(xsub, wg_c, we_c, k=cfg.k, EC=sub.EC, act=cfg.hidden_act)
+            torch_moe.moe_forward_cpu(xsub, wg_c, we_c, k=cfg.k, EC=ec, act=cfg.hidden_act)
         dt = (time.perf_counter() - t0) / iters
         line["cpu_baseline"] = {"value": tokens / dt, "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{iters} forwards of {tokens} of {S} tokens (plain torch CPU MoE forward, "
                                           f"oracle/torch_moe.py; {os.cpu_count()} host CPUs visible, {usable_cpus()} usable under the cgroup quota)"}
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line), flush=True)
-    return 0
+    pc = line.get("parity_check")
+    return 0 if (pc is None or pc["ok"]) else 4
 
 
 if __name__ == "__main__":

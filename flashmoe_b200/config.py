@@ -170,11 +170,28 @@ def load_config(path: Optional[os.PathLike] = None) -> MoEConfig:
     return from_dict(raw)
 
 
-# The five BASELINE.json configurations (SURVEY.md section 8 header / Appendix B).
+# The BASELINE.json configurations (SURVEY.md section 8 header / Appendix B).  A: CPU plumbing case; B: the single-GPU
+# headline; C: Mixtral-8x7B layer shape on 8 GPUs; D*: token sweep (32 experts, d_model 2048, ffn 2048 = the
+# reference's default intermediate_size, csrc/flashmoe_config.json:9); E*: expert sweep at 8192 tokens per rank.
+def _sweep(E: int, S: int) -> "MoEConfig":
+    return MoEConfig(num_experts=E, expert_top_k=2, sequence_len=S, hidden_size=2048, intermediate_size=2048)
+
+
 BASELINE_CONFIGS: Dict[str, MoEConfig] = {
     "A": MoEConfig(num_experts=2, expert_top_k=1, sequence_len=128, hidden_size=512, intermediate_size=2048),
     "B": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=4096, hidden_size=1024, intermediate_size=4096),
     "C": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=4096, hidden_size=4096, intermediate_size=14336),
-    "D4k": MoEConfig(num_experts=32, expert_top_k=2, sequence_len=4096, hidden_size=2048, intermediate_size=2048),
-    "E8": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=8192, hidden_size=2048, intermediate_size=2048),
+    "D1k": _sweep(32, 1024), "D4k": _sweep(32, 4096), "D16k": _sweep(32, 16384), "D64k": _sweep(32, 65536),
+    "E8": _sweep(8, 8192), "E16": _sweep(16, 8192), "E32": _sweep(32, 8192), "E64": _sweep(64, 8192),
+    "E128": _sweep(128, 8192),
+}
+
+CONFIG_DESCRIPTIONS: Dict[str, str] = {
+    "A": "configs[0]: 2 experts top-1 seq=128 d_model=512 ffn=2048 (CPU plumbing case)",
+    "B": "configs[1]: 8 experts top-2 seq=4096 d_model=1024 ffn=4096 bf16 (per rank); experts sharded E/N",
+    "C": "configs[2]: 8 experts top-2 seq=4096 d_model=4096 ffn=14336 bf16 (Mixtral-8x7B layer shape, per rank); experts sharded E/N",
+    **{f"D{n}": f"configs[3] token sweep: 32 experts top-2 seq={s} d_model=2048 ffn=2048 bf16 (per rank); experts sharded E/N"
+       for n, s in (("1k", 1024), ("4k", 4096), ("16k", 16384), ("64k", 65536))},
+    **{f"E{e}": f"configs[4] expert sweep: {e} experts top-2 seq=8192 d_model=2048 ffn=2048 bf16 (per rank); experts sharded E/N"
+       for e in (8, 16, 32, 64, 128)},
 }

@@ -629,6 +629,14 @@ FM_API int fm_symm_local_ptr(const fm_ctx_t* ctx, void** base) {
     return FM_OK;
 }
 
+FM_API int fm_output_buffer(const fm_ctx_t* ctx, void** ptr, size_t* bytes) {
+    if (ctx == nullptr || ptr == nullptr || bytes == nullptr) return fail(FM_EINVAL, "null argument");
+    const bool has = ctx->d.world > 1;   // the accumulation target peers add into; single rank: the caller's tensor
+    *ptr = has ? static_cast<char*>(ctx->symm) + ctx->off_out_acc : nullptr;
+    *bytes = has ? (size_t)ctx->d.S * ctx->d.H * 2 : 0;
+    return FM_OK;
+}
+
 FM_API int fm_symm_use_external(fm_ctx_t* ctx, void* base, size_t bytes) {
     if (ctx == nullptr || base == nullptr) return fail(FM_EINVAL, "null argument");
     if (ctx->attached && ctx->d.world > 1) return fail(FM_ESTATE, "already attached");

@@ -221,6 +221,23 @@ class MoEContext:
     def wait_host(self, ticket: int) -> None:
         _lib.check(self._L.fm_host_wait(self._ctx, int(ticket)))
 
+    def output_buffer(self) -> torch.Tensor:
+        """A [mini_batch, seq, H] bf16 tensor to pass as `out=`.  With world > 1 it aliases the region of this rank's
+        symmetric slab that the experts accumulate into, so `forward(..., out=ctx.output_buffer())` leaves the result in
+        place instead of copying it to a caller tensor at the end of the kernel (it is overwritten by the next forward
+        and dies with the context).  With world == 1 the kernel accumulates into any `out`; a fresh tensor is returned."""
+        shape = (self.cfg.mini_batch, self.cfg.sequence_len, self.dims["H"])
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(self._L.fm_output_buffer(self._ctx, ctypes.byref(ptr), ctypes.byref(nbytes)))
+        if not ptr.value:
+            return torch.empty(shape, dtype=torch.bfloat16, device=self.device)
+
+        class _Raw:  # CUDA array interface view of the slab region (int16 elements, reinterpreted below)
+            __cuda_array_interface__ = {"shape": (nbytes.value // 2,), "typestr": "<i2", "data": (ptr.value, False),
+                                        "version": 3}
+
+        return torch.as_tensor(_Raw(), device=self.device).view(torch.bfloat16).view(shape)
+
     def set_trace(self, enable: bool) -> None:
         _lib.check(self._L.fm_set_trace(self._ctx, 1 if enable else 0))
 

@@ -113,6 +113,12 @@ FM_API int fm_symm_use_external(fm_ctx_t* ctx, void* base, size_t bytes);
 FM_API int fm_moe_forward(fm_ctx_t* ctx, const void* x, const void* gate_w, const void* expert_w,
                           const void* bias_up, const void* bias_down, void* out, void* stream);
 
+/* world > 1: the [S,H] bf16 region of this rank's symmetric slab into which the experts (local and remote) accumulate
+ * this rank's output rows.  Passing exactly this pointer as `out` to fm_moe_forward leaves the result there and skips
+ * the final copy into a caller tensor (zero-copy output, like registering a user buffer with NVSHMEM); it is
+ * overwritten by the next forward.  world == 1: *ptr = NULL, *bytes = 0 (the kernel accumulates straight into `out`). */
+FM_API int fm_output_buffer(const fm_ctx_t* ctx, void** ptr, size_t* bytes);
+
 /* Same, with the activations in HOST memory (pinned for full PCIe speed): copies x host->device, runs the layer,
  * copies out device->host, then waits for the result (the reference's blocking behaviour,
  * python_bindings.cu:131-148).  Equivalent to fm_host_submit + fm_host_wait. */

@@ -204,6 +204,74 @@ def test_host_buffer_entry_point_equals_device_path():
     ctx.close()
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+def test_relaunch_with_changing_inputs_every_launch_checked(monkeypatch, fused):
+    """Back-to-back launches on ONE context with different activations (routing, per-expert counts and drops change,
+    including counts that shrink so the previous launch's rows lie beyond the new count): every launch's output is
+    compared with the oracle, so a read of stale recv_x / hidden / recv_meta / accumulator state cannot hide."""
+    monkeypatch.setenv("FM_FUSED_COMBINE", str(fused))
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=1024, hidden_size=256, intermediate_size=512, drop_tokens=0)
+    g = torch.Generator().manual_seed(77)
+    xs = [torch.randn(1, cfg.S, cfg.H, generator=g).bfloat16() for _ in range(3)]
+    xs[1][:, : cfg.S // 2] = xs[1][:, :1]        # half of the tokens identical: two experts get most rows
+    _, wg, we, _, _ = make_inputs(cfg, seed=78)
+    refs = [run_oracle(cfg, x, wg, we) for x in xs]
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    wgd, wed = wg.to(dev), we.to(dev)
+    for it in range(9):
+        i = (it * 2) % 3
+        out = ctx.forward(xs[i].to(dev), wgd, wed)
+        ctx.synchronize()
+        mism = check_topk(ctx.read("topk_idx"), refs[i])
+        check_output(mo.to_bits(out.cpu().reshape(cfg.S, cfg.H)), refs[i].out, rows_ok=~mism, what=f"launch {it}")
+        if not mism.any():
+            assert (ctx.read("counts") == refs[i].counts).all()
+    ctx.close()
+
+
+def test_pipelined_host_entry_point_matches_device_path():
+    """fm_host_submit / fm_host_wait: three steps in flight with different inputs; every result equals the device path."""
+    cfg = CASES["small_drop"]
+    g = torch.Generator().manual_seed(31)
+    xs = [torch.randn(1, cfg.S, cfg.H, generator=g).bfloat16() for _ in range(5)]
+    _, wg, we, _, _ = make_inputs(cfg, seed=32)
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    wgd, wed = wg.to(dev), we.to(dev)
+    want = []
+    for x in xs:
+        want.append(ctx.forward(x.to(dev), wgd, wed).cpu())
+    ctx.synchronize()
+    pins = [x.pin_memory() for x in xs]
+    outs = [torch.empty_like(x).pin_memory() for x in xs]
+    tickets = []
+    for i in range(5):
+        if len(tickets) == 3:
+            ctx.wait_host(tickets.pop(0))
+        tickets.append(ctx.submit_host(pins[i], wgd, wed, outs[i]))
+    with pytest.raises(RuntimeError):  # tickets complete in submission order
+        ctx.wait_host(tickets[-1])
+    for t in tickets:
+        ctx.wait_host(t)
+    for i in range(5):
+        assert torch.equal(outs[i], want[i]), f"step {i}"
+    ctx.close()
+
+
+def test_misaligned_tensor_is_rejected():
+    cfg = CASES["tiny"]
+    x, wg, we, _, _ = make_inputs(cfg, seed=33)
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    buf = torch.empty(x.numel() + 8, dtype=torch.bfloat16, device=dev)
+    x_off = buf[1: 1 + x.numel()].view(x.shape)   # contiguous, but starts 2 bytes into the allocation
+    x_off.copy_(x)
+    with pytest.raises(RuntimeError, match="16-byte"):
+        ctx.forward(x_off, wg.to(dev), we.to(dev))
+    ctx.close()
+
+
 def test_reference_style_argument_checks_raise_runtime_error():
     cfg = CASES["tiny"]
     x, wg, we, _, _ = make_inputs(cfg, seed=22)
