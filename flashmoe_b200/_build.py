@@ -26,6 +26,16 @@ STAMP_PATH = PKG_DIR / ".build_stamp.json"
 SOURCES = [CSRC / "flashmoe_b200.cu"]
 HEADERS = [CSRC / "fm_kernel.cuh", CSRC / "fm_ptx.cuh", REPO_ROOT / "include" / "flashmoe_b200.h"]
 
+# the compiled `flashmoe._C` extension (csrc/python_bindings.cu: pybind11 over the C-ABI; no device code, no torch headers)
+BINDINGS_SRC = REPO_ROOT / "csrc" / "python_bindings.cu"
+
+
+def ext_path() -> Path:
+    import sysconfig
+
+    return REPO_ROOT / "flashmoe" / ("_C" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "--compiler-options", "-fPIC,-fvisibility=hidden", "-shared",
@@ -81,6 +91,36 @@ def build(config_path: Optional[os.PathLike] = None, force: bool = False, verbos
     return LIB_PATH
 
 
+def build_bindings(force: bool = False, verbose: bool = False) -> Path:
+    """Compile csrc/python_bindings.cu into flashmoe/_C<ext suffix>, linked against the in-tree libflashmoe_b200.so
+    (found at run time through an $ORIGIN-relative rpath).  Needs pybind11 (present in this image)."""
+    import sysconfig
+
+    import pybind11
+
+    out = ext_path()
+    stamp = out.with_suffix(".stamp")
+    h = hashlib.sha256(BINDINGS_SRC.read_bytes() + (REPO_ROOT / "include" / "flashmoe_b200.h").read_bytes()).hexdigest()
+    if not force and out.exists() and stamp.exists() and stamp.read_text() == h and LIB_PATH.exists():
+        return out
+    if not LIB_PATH.exists():
+        raise RuntimeError("build libflashmoe_b200.so first")
+    cmd = [find_nvcc(), "-std=c++17", "-O2", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+           "--compiler-options", "-fPIC,-fvisibility=hidden", "-shared",
+           f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}", f"-I{REPO_ROOT / 'include'}",
+           "-o", str(out), str(BINDINGS_SRC), f"-L{PKG_DIR}", "-lflashmoe_b200",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../flashmoe_b200"]
+    if Path("/usr/bin/g++").exists():
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on python_bindings.cu ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    stamp.write_text(h)
+    return out
+
+
 def lib_is_current(config_path: Optional[os.PathLike] = None) -> bool:
     try:
         cfg = _config.load_config(config_path)
@@ -91,3 +131,4 @@ def lib_is_current(config_path: Optional[os.PathLike] = None) -> bool:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_bindings(force="--force" in sys.argv, verbose=True))

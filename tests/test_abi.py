@@ -99,7 +99,11 @@ def test_reference_api_surface_is_mirrored():
 
     for fn in ("moe_forward", "initialize", "finalize", "get_compiled_config", "get_bookkeeping", "get_num_local_experts"):
         assert callable(getattr(_C, fn))
-    assert list(inspect.signature(_C.moe_forward).parameters) == ["input", "gate_weights", "expert_weights"]
+    # compiled extension: the keyword names are in the pybind11 docstring signature; the ctypes fallback has a Python signature
+    from flashmoe_b200 import _C as _C_ctypes
+
+    assert list(inspect.signature(_C_ctypes.moe_forward).parameters) == ["input", "gate_weights", "expert_weights"]
+    assert "moe_forward(input: object, gate_weights: object, expert_weights: object)" in _C.moe_forward.__doc__
     assert set(_C.get_compiled_config()) == {"S", "H", "E", "P", "PX", "Element_size"}
     with pytest.raises(RuntimeError, match="initialize"):
         _C.moe_forward(None, None, None)
@@ -124,3 +128,28 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(root, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "moe_oracle" not in text, f
+
+
+def test_flashmoe_C_is_the_compiled_extension_with_the_reference_signatures():
+    """`flashmoe._C` is built from csrc/python_bindings.cu (reference csrc/python_bindings.cu:194-217): six functions,
+    the reference's keyword names, RuntimeError (not exit) when used before initialize()."""
+    from flashmoe_b200 import _build
+
+    _build.build_bindings()
+    import importlib
+
+    import flashmoe
+
+    ext = importlib.import_module("flashmoe._C")
+    assert ext.__file__.endswith(".so")
+    for fn in ("moe_forward", "initialize", "finalize", "get_compiled_config", "get_bookkeeping", "get_num_local_experts"):
+        assert callable(getattr(ext, fn))
+    doc = ext.moe_forward.__doc__
+    assert "input" in doc and "gate_weights" in doc and "expert_weights" in doc
+    cc = ext.get_compiled_config()
+    assert cc == C.load_config().compiled_dict() and set(cc) == {"S", "H", "E", "P", "PX", "Element_size"}
+    with pytest.raises(RuntimeError, match="initialize"):
+        ext.moe_forward(input=None, gate_weights=None, expert_weights=None)
+    with pytest.raises(RuntimeError):
+        ext.get_num_local_experts()
+    assert flashmoe.get_compiled_config() == cc

@@ -294,18 +294,26 @@ def test_reference_style_argument_checks_raise_runtime_error():
 
 
 def test_module_level_C_api_single_process():
-    """flashmoe._C.initialize / moe_forward / finalize on the compiled configuration (config B)."""
+    """flashmoe._C (the COMPILED pybind11 extension, csrc/python_bindings.cu) initialize / moe_forward / finalize on the
+    compiled configuration (config B), output checked against the oracle."""
     import flashmoe
     from flashmoe import _C
 
+    assert _C.__file__.endswith(".so")
     _C.initialize()
     try:
         cc = flashmoe.get_compiled_config()
         assert cc["S"] == 4096 and cc["Element_size"] == 2 and _C.get_bookkeeping() == {"nLx": 8}
+        assert _C.get_num_local_experts() == 8
         cfg = BASELINE_CONFIGS["B"]
         x, wg, we, _, _ = make_inputs(cfg, seed=23)
-        out = _C.moe_forward(x.cuda(), wg.cuda(), we.cuda())
+        out = _C.moe_forward(input=x.cuda(), gate_weights=wg.cuda(), expert_weights=we.cuda())
         assert out.shape == x.shape and out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()
+        ref = run_oracle(cfg, x, wg, we)
+        # the extension does not expose the routing tables: compare all rows, allowing for the (rare) ambiguous tokens
+        check_output(mo.to_bits(out.cpu().reshape(cfg.S, cfg.H)), ref.out, rows_ok=~ref.ambiguous)
+        with pytest.raises(RuntimeError, match="compiled S"):
+            _C.moe_forward(x[:, :64].contiguous().cuda(), wg.cuda(), we.cuda())
         with pytest.raises(RuntimeError):
             _C.initialize()
     finally:
