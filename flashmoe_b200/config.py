@@ -129,8 +129,8 @@ class MoEConfig:
         """Constraints the kernels rely on (reference asserts: bootstrap.cuh:542-544, types.cuh:496)."""
         if self.torch_dtype != DTYPE_BF16:
             raise ConfigError("this build computes in bf16 only (torch_dtype must be 2)")
-        if self.is_training:
-            raise ConfigError("is_training=1 (aux-loss accumulation) is not implemented; forward-only build")
+        if self.is_training not in (0, 1):
+            raise ConfigError("is_training must be 0 or 1")
         if self.S % BLOCK_M:
             raise ConfigError(f"S={self.S} must be a multiple of {BLOCK_M}")
         if self.H % 64 or self.P % 64:

@@ -141,6 +141,9 @@ struct fm_ctx {
     size_t symm_bytes = 0, off_recv_x = 0, off_ret_y = 0, off_recv_flag = 0, off_ret_flag = 0;
     size_t off_recv_meta = 0, off_out_acc = 0, off_done_flag = 0, off_recv_rows = 0;
     bool fused = false;   // GEMM1 epilogue adds straight into the source rank's output (no return buffer / gather)
+    bool dense = false;   // E == 1: GEMM0 reads x in place, no router GEMV, no dispatch copy (reference fffn.cuh:31-167)
+    float* aux = nullptr; // is_training: [2][2E+1] {gML, gMeC, loss} by epoch parity
+    const void* cached_x = nullptr;
     unsigned int* pkt_done = nullptr;
     void* peer_base[FM_MAX_WORLD] = {};
     bool peer_opened[FM_MAX_WORLD] = {};
@@ -159,7 +162,7 @@ namespace {
 
 int validate_config(const fm_config_t& c, int world, fm_dims_t* d) {
     if (c.torch_dtype != 2) return fail(FM_EINVAL, "torch_dtype=%d: this build computes in bf16 only (2)", c.torch_dtype);
-    if (c.is_training != 0) return fail(FM_EINVAL, "is_training=1 is not implemented (forward-only build)");
+    if (c.is_training != 0 && c.is_training != 1) return fail(FM_EINVAL, "is_training must be 0 or 1");
     if (c.hidden_act != 0 && c.hidden_act != 1) return fail(FM_EINVAL, "hidden_act must be 0 (relu) or 1 (gelu)");
     if (c.drop_tokens != 0 && c.drop_tokens != 1) return fail(FM_EINVAL, "drop_tokens must be 0 or 1");
     if (c.capacity_factor < 1) return fail(FM_EINVAL, "capacity_factor must be >= 1");
@@ -258,9 +261,13 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     const fm_dims_t& d = c->d;
     const int nLx = d.num_local_experts;
     int rc;
+    if (c->dense && c->cached_x != x) {   // E == 1: the A operand of GEMM0 is the caller's x itself
+        if ((rc = make_tmap(&c->tm_a0, x, (uint64_t)d.S, d.H, fm::BLOCK_M))) return rc;
+        c->cached_x = x;
+    }
     if (!c->tm_static_ready) {
-        if ((rc = make_tmap(&c->tm_a0, static_cast<char*>(c->symm) + c->off_recv_x, (uint64_t)c->num_pkts * d.pEC, d.H,
-                            fm::BLOCK_M)))
+        if (!c->dense && (rc = make_tmap(&c->tm_a0, static_cast<char*>(c->symm) + c->off_recv_x, (uint64_t)c->num_pkts * d.pEC, d.H,
+                                         fm::BLOCK_M)))
             return rc;
         if ((rc = make_tmap(&c->tm_a1, c->hidden, (uint64_t)c->num_pkts * d.pEC, d.P, fm::BLOCK_M))) return rc;
         c->tm_static_ready = true;
@@ -317,6 +324,8 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     // single rank: accumulate straight into the caller's tensor; otherwise into the peer-mapped accumulator
     p.out_acc = d.world == 1 ? p.out : reinterpret_cast<__nv_bfloat16*>(sb + c->off_out_acc);
     if (d.world == 1) p.peer_out_acc[0] = p.out;
+    p.aux = c->aux;
+    p.dense = c->dense ? 1 : 0;
     p.dbg = c->dbg_dev;
     p.trace = c->trace_on ? c->trace : nullptr;
 
@@ -419,6 +428,11 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->cfg = c;
     ctx->d = d;
     ctx->device = device;
+    // tuning knobs (tile widths of the two GEMMs, scheduler look-ahead); environment overrides are for experiments
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return (v != nullptr && *v) ? atoi(v) : dflt;
+    };
     ctx->grid = d.num_sms;  // one persistent CTA per SM; all co-resident (spin waits + grid barrier)
     {
         const char* v = getenv("FM_PAIR");
@@ -428,6 +442,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         // k > 2 keeps the gather so results do not depend on arrival order
         const char* f = getenv("FM_FUSED_COMBINE");
         ctx->fused = ((f != nullptr && *f) ? atoi(f) != 0 : true) && d.k <= 2;
+        ctx->dense = d.E == 1 && world == 1 && env_int("FM_DENSE_E1", 1) != 0;
         if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
         ctx->d.grid = ctx->grid;
     }
@@ -437,11 +452,6 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         return fail(FM_EINVAL, "tokens-per-CTA * k = %d exceeds the router scratch (%d)", ctx->tpc * d.k, fm::G_SEL_MAX);
     }
     const int nLx = d.num_local_experts;
-    // tuning knobs (tile widths of the two GEMMs, scheduler look-ahead); environment overrides are for experiments
-    auto env_int = [](const char* name, int dflt) {
-        const char* v = getenv(name);
-        return (v != nullptr && *v) ? atoi(v) : dflt;
-    };
     ctx->bn0 = env_int("FM_BN0", 256) == 128 ? 128 : 256;
     ctx->bn1 = env_int("FM_BN1", 256) == 128 ? 128 : 256;
     ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 8);
@@ -543,6 +553,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     FM_TRY_CUDA(cudaMemcpy(ctx->blocks, blocks.data(), blocks.size() * sizeof(fm::TileBlock), cudaMemcpyHostToDevice));
     FM_TRY(dev_alloc(&ctx->hidden, (size_t)ctx->num_pkts * d.pEC * d.P));
     FM_TRY(dev_alloc(&ctx->trace, (size_t)ctx->grid * fm::TRACE_SLOTS));
+    if (c.is_training) FM_TRY(dev_alloc(&ctx->aux, (size_t)2 * (2 * d.E + 1)));
 
     // symmetric slab: [recv_x | ret_y | recv_flag | ret_flag]  (reference heap + flags, bootstrap.cuh:348-362)
     size_t off = 0;
@@ -588,7 +599,8 @@ FM_API int fm_destroy(fm_ctx_t* ctx) {
     for (int r = 0; r < ctx->d.world; ++r)
         if (ctx->peer_opened[r] && ctx->peer_base[r] != nullptr) cudaIpcCloseMemHandle(ctx->peer_base[r]);
     void* bufs[] = {ctx->topk_idx, ctx->topk_w, ctx->mcw, ctx->slot, ctx->counts, ctx->gate_out, ctx->chunk_counts,
-                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->pkt_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace};
+                    ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->pkt_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace,
+                    ctx->aux};
     for (void* b : bufs)
         if (b != nullptr) cudaFree(b);
     for (int i = 0; i < FM_HOST_SLOTS; ++i) {
@@ -809,6 +821,9 @@ static int buffer_desc(const fm_ctx_t* c, int which, const void** ptr, size_t* b
         case FM_BUF_GATE_OUT: *ptr = c->gate_out; *bytes = (size_t)d.S * d.E * 2; break;
         case FM_BUF_RECV_CNT: *ptr = c->recv_cnt; *bytes = (size_t)c->num_pkts * 4; break;
         case FM_BUF_TRACE: *ptr = c->trace; *bytes = (size_t)c->grid * fm::TRACE_SLOTS * 8; break;
+        case FM_BUF_AUX_LOSS:
+            if (c->aux == nullptr) return fail(FM_EINVAL, "the auxiliary loss exists only with is_training = 1");
+            *ptr = c->aux + (size_t)(c->epoch & 1u) * (2 * d.E + 1); *bytes = (size_t)(2 * d.E + 1) * 4; break;
         default: return fail(FM_EINVAL, "unknown buffer id %d", which);
     }
     return FM_OK;

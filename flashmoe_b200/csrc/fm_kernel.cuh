@@ -45,8 +45,10 @@ constexpr int NUM_WARPS = NUM_THREADS / 32;
 constexpr int EPI_WARP0 = 4;   // warps 4..11: warp % 4 selects the TMEM lane quarter, (warp - 4) / 4 the column half
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators per CTA (double-buffered against the epilogue)
-constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..15] sub-phase stamps, [16+i] tile i ready,
-                                 // [64+i] tile i stored, [112+i] tile i claimed (i < 8), [120..124] epilogue of tile 2
+constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..12] sub-phase stamps; per tile i < 16 of this CTA (pair):
+                                 // [16+i] dependencies resolved (scheduler), [32+i] first k-block landed, [48+i] last MMA
+                                 // issued (MMA thread), [64+i] accumulator complete (epilogue sees tmem_full), [80+i]
+                                 // epilogue stores issued, [96+i] published, [112+i] claimed (scheduler)
 
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;                  // 16 KiB
 constexpr int PIPE_BYTES = 196608;                                    // 4 x 48 KiB (solo) = 6 x 32 KiB (CTA pair)
@@ -150,6 +152,10 @@ struct FmParams {
     uint4* peer_recv_meta[FM_MAX_WORLD];
     unsigned long long* peer_done_flag[FM_MAX_WORLD];
     __nv_bfloat16* peer_out_acc[FM_MAX_WORLD];
+    // training mode (is_training = 1): [2][2E+1] f32 by epoch parity = {gML[E] mean gate probability per expert,
+    // gMeC[E] mean routed fraction per expert, loss} (reference moe/gate.cuh:608-635,698-706,763-773); nullptr otherwise
+    float* aux;
+    int dense;          // E == 1: no router GEMV, no dispatch copy; GEMM0 reads x in place (reference moe/fffn.cuh:31-167)
     DebugRecord* dbg;
     unsigned long long* trace;  // optional [grid][TRACE_SLOTS] %globaltimer stamps (nullptr = off)
 };
@@ -201,6 +207,28 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 //   Slots: ascending-token order within the CTA's chunk here; chunk bases after the grid barrier (a legal
 //   interleaving of the reference's BlockScan + atomicAdd(eC) order, gate.cuh:678-718).
 // ============================================================================================================
+// E == 1 (reference: the dense fffn kernel is selected instead of the MoE kernel, moe.cuh:174-177): every token goes to
+// expert 0 with probability 1, slot = token index, nothing is dropped (EC >= S).  No GEMV, no softmax.
+__device__ __forceinline__ void gate_phase_dense(const FmParams& p, int t0, int n_tok) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n_tok; i += NUM_THREADS) {
+        const int t = t0 + i;
+        p.topk_idx[t] = 0;
+        p.topk_w[t] = __float2bfloat16_rn(1.0f);
+        p.mcw[t] = 1.0f;
+        p.gate_out[t] = __float2bfloat16_rn(1.0f);
+        p.slot[t] = t;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        p.counts[0] = p.S;
+        p.recv_cnt[0] = p.S;
+        if (p.aux != nullptr) {   // mean probability 1, routed fraction 1, loss 1 * 1 / 1
+            float* a = p.aux + (size_t)(p.epoch & 1u) * 3;
+            a[0] = 1.0f; a[1] = 1.0f; a[2] = 1.0f;
+        }
+    }
+}
+
 __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = p.E, H = p.H, k = p.k;
@@ -208,6 +236,10 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     float* logit_s = reinterpret_cast<float*>(smem + G_OFF_LOGIT);
     int16_t* sel_e = reinterpret_cast<int16_t*>(smem + G_OFF_SEL);
     int* rank_s = reinterpret_cast<int*>(smem + G_OFF_SEL + G_SEL_MAX * 2);
+
+    float* aux_s = reinterpret_cast<float*>(smem + G_OFF_BASE + 8192);   // training: this chunk's sum_t p[t,e]
+    if (p.aux != nullptr)
+        for (int e = tid; e < E; e += NUM_THREADS) aux_s[e] = 0.0f;   // ordered by the block syncs of the first stage below
 
     const int EG = E < 128 ? E : 128;                      // experts staged per group
     int Hc = (G_WG_BYTES / (EG * 2)) & ~255;               // H columns staged per chunk (multiple of 256)
@@ -353,8 +385,24 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             p.mcw[t] = sum;
         }
         __syncthreads();
+        if (p.aux != nullptr) {
+            // column sums of the fp32 probabilities of this sub-chunk (the reference block-reduces each gate tile's
+            // columns, gate.cuh:611-627): warp w owns experts w, w + NUM_WARPS, ...; lanes stride over the tokens
+            for (int e = warp; e < E; e += NUM_WARPS) {
+                float acc = 0.0f;
+                for (int ti = lane; ti < n_sub; ti += 32) acc += logit_s[ti * ldl + e];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) aux_s[e] += acc;
+            }
+            __syncthreads();
+        }
     }
     if (tid == 0) trace_stamp(p, 12);
+    if (p.aux != nullptr) {   // gML[e] += (sum over this chunk) / S   (gate.cuh:628-634: atomicAdd(gML + e, colAgg / S))
+        float* gml = p.aux + (size_t)(p.epoch & 1u) * (2 * E + 1);
+        for (int e = tid; e < E; e += NUM_THREADS) atomicAdd(gml + e, __fdividef(aux_s[e], (float)p.S));
+    }
     // position of every (token, pick) among this chunk's selections of the same expert, ascending (token, pick) order.
     // One warp walks the entries 32 at a time: lanes holding the same expert find each other with match.any, the rank
     // inside the group is a popcount, the running per-expert count lives in shared memory (O(n) instead of O(n^2);
@@ -435,6 +483,16 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         const int owner = e / p.nLx, le = e - owner * p.nLx;
         st_relaxed_sys_u64(p.peer_recv_flag[owner] + (size_t)p.rank * p.nLx + le,
                            ((unsigned long long)p.epoch << 32) | (unsigned int)rows);
+        if (p.aux != nullptr) {
+            // gMeC[e] = selections of e / S (gate.cuh:698-706 adds each tile's count / S; the chunk totals are summed
+            // first here), loss += gML[e] * gMeC[e] / E (gate.cuh:763-773).  Every CTA's gML atomics precede its arrival
+            // at the grid barrier, so gML is complete here.
+            float* a = p.aux + (size_t)(p.epoch & 1u) * (2 * E + 1);
+            const float ce = __fdividef((float)tot, (float)p.S);
+            a[E + e] = ce;
+            const float me = *reinterpret_cast<volatile float*>(a + e);
+            atomicAdd(a + 2 * E, __fdividef(me * ce, (float)E));
+        }
     }
     // Row copies through the TMA engine: the chunk's token rows are contiguous in x, so one bulk load stages up to
     // 128 KiB of them in shared memory and every kept (token, pick) pair is one bulk store of a whole row into the
@@ -571,16 +629,16 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
-                if (n < 8) trace_stamp(p, 112 + n);   // claim time of tile n (ready time is slot 16+n)
+                if (n < 16) trace_stamp(p, 112 + n);   // claim time of tile n (ready time is slot 16+n)
                 while (id >= p.blocks[cursor + 1].start) ++cursor;
                 const TileBlock blk = p.blocks[cursor];
                 const int local = id - blk.start;
                 const int mblk = (local % tcm_items) * mstep, nt = local / tcm_items;
                 const int src = blk.pkt / p.nLx, le = blk.pkt - src * p.nLx;
                 // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
-                unsigned long long f;
+                unsigned long long f = ((unsigned long long)p.epoch << 32) | (unsigned int)p.S;   // dense: all S rows, in x
                 bool stale = false;
-                {
+                if (!p.dense) {
                     SpinGuard g;
                     for (;;) {
                         f = ld_acquire_sys_u64(p.recv_flag + blk.pkt);
@@ -595,7 +653,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 }
                 if (stale) continue;
                 const int cnt = (int)(f & 0xffffffffull);
-                if (local == 0 && blk.kind == 0) p.recv_cnt[blk.pkt] = cnt;
+                if (local == 0 && blk.kind == 0 && !p.dense) p.recv_cnt[blk.pkt] = cnt;
                 if (p.fused && local == 0 && blk.kind == 1 && cnt == 0)   // nothing to contribute: tell the source now
                     st_release_sys_u64(p.peer_done_flag[src] + (size_t)(p.rank * p.nLx + le),
                                        (unsigned long long)p.epoch << 32);
@@ -610,7 +668,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                         while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
                             g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, blk.pkt, mblk + r, 0);
                     }
-                } else if (p.phase_mask & 1u) {  // GEMM0 needs its row blocks of the packet to have landed (dispatch acks)
+                } else if ((p.phase_mask & 1u) && !p.dense) {  // GEMM0 needs its row blocks of the packet to have landed (dispatch acks)
                     for (int r = 0; r < mstep; ++r) {
                         const int need = r == 0 ? rows0 : rows1;
                         if (need == 0) break;
@@ -631,7 +689,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 ti.b_row = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * ti.bn;
                 break;
             }
-            if (ti.kind >= 0 && n < 48) trace_stamp(p, 16 + n);
+            if (ti.kind >= 0 && n < 16) trace_stamp(p, 16 + n);
             mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
             ring[q] = ti;
             if (PAIR) {  // mirror the descriptor into the peer CTA's ring over DSMEM, then signal both rings
@@ -741,8 +799,7 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
     uint64_t* sched_empty = bars + BAR_SCHED_EMPTY;
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
-    int stage = 0, phase = 0, q = 0, qphase = 0, as = 0, aphase = 0;
-    bool first_tile = true;
+    int stage = 0, phase = 0, q = 0, qphase = 0, as = 0, aphase = 0, nt = 0;
     for (;;) {
         int kind = -1, nk = 0, bn = BLOCK_N;
         if (lane == 0) {
@@ -762,7 +819,7 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
             const uint32_t d_tmem = tmem_base + (uint32_t)as * BLOCK_N;
             for (int kb = 0; kb < nk; ++kb) {
                 mbar_wait(&full[stage], phase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, stage);
-                if (first_tile && (kb == 0 || kb == 4 || kb == nk - 1)) trace_stamp(p, kb == 0 ? 13 : (kb == 4 ? 14 : 15));
+                if (kb == 0 && nt < 16) trace_stamp(p, 32 + nt);
                 tcgen05_fence_after();
                 const uint32_t sa = smem_u32(smem + stage * PC::STAGE_BYTES);
                 const uint64_t da = umma_smem_desc_sw128(sa);
@@ -782,9 +839,10 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
             }
             // accumulator complete -> epilogue warps (of both CTAs in pair mode)
             if (PAIR) umma_commit_pair(&tmem_full[as]); else umma_commit(&tmem_full[as]);
+            if (nt < 16) trace_stamp(p, 48 + nt);
         }
         if (++as == 2) { as = 0; aphase ^= 1; }
-        first_tile = false;
+        ++nt;
         __syncwarp();
     }
 }
@@ -876,7 +934,6 @@ __device__ __forceinline__ void drain_accumulator(const FmParams& p, const Drain
             }
         }
         __syncwarp();
-        if (a.stamp && c == a.c0) trace_stamp(p, 121);
     }
 }
 
@@ -930,7 +987,9 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         const bool fuse = p.fused != 0 && ti.kind == 1;
         int my_tok = 0;
         float my_pw = 0.0f, my_mcw = 1.0f;
-        if (fuse && quarter * 32 + lane < my_rows) {
+        if (fuse && p.dense) {
+            my_tok = my_mblk * BLOCK_M + quarter * 32 + lane;   // row i of the only packet IS token i
+        } else if (fuse && quarter * 32 + lane < my_rows) {
             const uint4 m = ld_global_v4(p.recv_meta + (size_t)ti.pkt * p.pEC + (size_t)my_mblk * BLOCK_M + quarter * 32 + lane);
             my_tok = (int)m.x;
             my_pw = __uint_as_float(m.y);
@@ -940,15 +999,15 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
-        const bool stamp_tile = (ntiles == 2) && tid == EPI_WARP0 * 32;
-        if (stamp_tile) trace_stamp(p, 120);
+        const bool stamp_tile = ntiles < 16 && tid == EPI_WARP0 * 32;
+        if (stamp_tile) trace_stamp(p, 64 + ntiles);
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * BLOCK_N;
         if (c1 > c0) {
             DrainArgs da;
             da.stg = stg; da.t_row = t_row; da.c0 = c0; da.c1 = c1; da.lane = lane; da.quarter = quarter;
             da.my_rows = my_rows; da.N = N; da.n0 = n0; da.bias = bias; da.out_rows = out_rows; da.acc_base = acc_base;
             da.my_tok = my_tok; da.my_pw = my_pw; da.my_mcw = my_mcw; da.release_bar = &tmem_empty[as]; da.crank = crank;
-            da.stamp = stamp_tile;
+            da.stamp = false;
             // one specialised instantiation per (epilogue kind, bias) pair: no per-element or per-group branching
             const int mode = ti.kind == 0 ? (p.act == 0 ? EPI_G0_RELU : EPI_G0_GELU)
                                           : (!fuse ? EPI_G1_STORE : (p.k > 1 ? EPI_G1_FUSED_ADD : EPI_G1_FUSED_COPY));
@@ -974,7 +1033,7 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             __syncwarp();
             if (lane == 0) release_to_leader<PAIR>(&tmem_empty[as], crank);
         }
-        if (stamp_tile) trace_stamp(p, 122);
+        if (stamp_tile) trace_stamp(p, 80 + ntiles);
         if (++as == 2) { as = 0; aphase ^= 1; }
 
         // hand the tile to the publisher: this warp's stores are issued (h will be read through the async proxy)
@@ -985,10 +1044,6 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
             mbar_arrive(&pub_full[ps]);
         }
         if (++ps == 2) { ps = 0; pphase ^= 1; }
-        if (tid == EPI_WARP0 * 32) {
-            if (ntiles < 48) trace_stamp(p, 64 + ntiles);
-            if (ntiles == 2) trace_stamp(p, 123);
-        }
         ++ntiles;
     }
 }
@@ -1043,7 +1098,7 @@ __device__ __forceinline__ void ffn_publisher(const FmParams& p, uint8_t* smem, 
                         }
                     }
                 }
-                if (ntiles == 2) trace_stamp(p, 124);
+                if (ntiles < 16) trace_stamp(p, 96 + ntiles);
             }
         }
         kind = __shfl_sync(0xffffffffu, kind, 0);
@@ -1285,9 +1340,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
             // peer can write them yet (a rank starts forward epoch+1 only after this launch has returned all its rows)
             unsigned int* next_rows = p.recv_rows + (size_t)((p.epoch + 1u) & 1u) * p.num_pkts * p.TCM;
             for (int i = tid; i < p.num_pkts * p.TCM; i += NUM_THREADS) next_rows[i] = 0u;
+            if (p.aux != nullptr) {   // the loss buffers of the next launch (reference clearState, moe.cuh:49-54)
+                float* next_aux = p.aux + (size_t)((p.epoch + 1u) & 1u) * (2 * p.E + 1);
+                for (int i = tid; i < 2 * p.E + 1; i += NUM_THREADS) next_aux[i] = 0.0f;
+            }
             if (tid == 0) *p.claim = 0u;
         }
-        gate_phase(p, smem, t0, n_tok);
+        if (p.dense) gate_phase_dense(p, t0, n_tok); else gate_phase(p, smem, t0, n_tok);
         if (tid == 0) trace_stamp(p, 1);
         grid_barrier(p);   // also a cluster-wide sync: the partner CTA's barriers are initialised before any remote arrive
         if (tid == 0) trace_stamp(p, 2);
@@ -1301,7 +1360,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
     // warps 4-7 then become the epilogue.
     const bool disp_warp = (warp == 2) || (warp >= EPI_WARP0);
     if ((p.phase_mask & 1u) && disp_warp) {
-        dispatch_phase(p, smem, t0, n_tok);
+        if (!p.dense) dispatch_phase(p, smem, t0, n_tok);
+        else if (warp == 2 && (tid & 31) == 0)   // nothing to copy: GEMM0's TMA reads x in place; release the producer
+            mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
         if (warp == 2 && (tid & 31) == 0) trace_stamp(p, 3);
     }
     if (p.phase_mask & 2u) {

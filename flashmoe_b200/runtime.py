@@ -29,6 +29,7 @@ _BUFFER_SPECS = {
     "gate_out": (_lib.BUF_GATE_OUT, np.uint16),
     "recv_cnt": (_lib.BUF_RECV_CNT, np.int32),
     "trace": (_lib.BUF_TRACE, np.uint64),
+    "aux_loss": (_lib.BUF_AUX_LOSS, np.float32),
 }
 
 
@@ -263,7 +264,7 @@ class MoEContext:
         npk = d["world"] * d["num_local_experts"]
         shapes = {"topk_idx": (S, k), "topk_w": (S, k), "mcw": (S,), "slot": (S, k), "counts": (E,),
                   "recv_x": (npk, d["pEC"], H), "hidden": (npk, d["pEC"], P), "ret_y": (E, d["pEC"], H),
-                  "gate_out": (S, E), "recv_cnt": (npk,), "trace": (d["grid"], 128)}
+                  "gate_out": (S, E), "recv_cnt": (npk,), "trace": (d["grid"], 128), "aux_loss": (2 * E + 1,)}
         return arr.reshape(shapes[name])
 
     @property

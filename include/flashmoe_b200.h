@@ -154,7 +154,9 @@ enum fm_buffer {
     FM_BUF_RET_Y = 7,    /* bf16  [E, pEC, H]       expert outputs returned to this rank */
     FM_BUF_GATE_OUT = 8, /* bf16  [S, E]  full softmax row (reference gateOut[S,PX] without the padding columns) */
     FM_BUF_RECV_CNT = 9, /* int32 [W, nLx] rows received per (source rank, local expert) in the last forward */
-    FM_BUF_TRACE = 10    /* u64   [grid, 128] %globaltimer stamps of the last forward (fm_set_trace) */
+    FM_BUF_TRACE = 10,   /* u64   [grid, 128] %globaltimer stamps of the last forward (fm_set_trace) */
+    FM_BUF_AUX_LOSS = 11 /* f32   [2E+1] is_training = 1 only: gML[E] (mean gate probability per expert), gMeC[E] (mean
+                            routed fraction per expert), loss = sum_e gML*gMeC / E  (moe/gate.cuh:608-635,698-706,763-773) */
 };
 FM_API int fm_buffer_bytes(const fm_ctx_t* ctx, int which, size_t* bytes);
 FM_API int fm_read_buffer(fm_ctx_t* ctx, int which, void* host_dst, size_t bytes);

@@ -463,3 +463,26 @@ done:
     free(rows); free(hbuf); free(ybuf); free(yoff); free(fill); free(rowpos); free(probs);
     return rc;
 }
+
+/* ------------------------------------------------------------------ training-mode auxiliary (load-balancing) loss
+ * JobType::training only (is_training = 1).  The reference accumulates, per launch (buffers cleared by clearState,
+ * moe/moe.cuh:49-54; layout gML[E] | gMeC[E] | gL, types.cuh:936-958):
+ *   gML[e]  = sum over 128-token gate tiles of (column sum of the fp32 softmax probabilities of the tile) / S
+ *             (moe/gate.cuh:608-635: BlockReduce per column, atomicAdd(gML + e, colAgg / S))  = mean_t p[t,e]
+ *   gMeC[e] = sum over tiles of (selections of e in the tile) / S   (moe/gate.cuh:698-706)  = counts[e] / S, counting
+ *             every selection, dropped or not
+ *   gL      = sum_e gML[e] * gMeC[e] / E                              (moe/gate.cuh:763-773)
+ * fp32 atomics in arrival order in the reference; double accumulation here (compare with a relative tolerance).
+ * probs f32 [S,E] (fmo_gate's output), counts i32 [E] (fmo_slots' output).
+ */
+FMO_API void fmo_aux_loss(const float* probs, const int32_t* counts, int S, int E, float* gML, float* gMeC, float* loss) {
+    double l = 0.0;
+    for (int e = 0; e < E; ++e) {
+        double acc = 0.0;
+        for (int t = 0; t < S; ++t) acc += (double)probs[(size_t)t * E + e];
+        gML[e] = (float)(acc / (double)S);
+        gMeC[e] = (float)((double)counts[e] / (double)S);
+        l += (double)gML[e] * (double)gMeC[e] / (double)E;
+    }
+    *loss = (float)l;
+}

@@ -206,6 +206,37 @@ def forward_sample(x: np.ndarray, wg_eff: np.ndarray, w_up: np.ndarray, w_down_e
     return OracleResult(out, topk, slot, kept, counts, mcw, gate_out, logits, ambiguity_flags(logits, abs_sum, k))
 
 
+def aux_loss(x: np.ndarray, wg_eff: np.ndarray, *, k: int, EC: int):
+    """Training-mode auxiliary loss of one rank's tokens: (gML [E], gMeC [E], loss) as float32
+    (reference moe/gate.cuh:608-635,698-706,763-773; see fmo_aux_loss)."""
+    S, H = x.shape
+    E = wg_eff.shape[0]
+    logits = np.zeros((S, E), dtype=np.float32)
+    probs = np.zeros((S, E), dtype=np.float32)
+    gate_out = np.zeros((S, E), dtype=np.uint16)
+    topk = np.zeros((S, k), dtype=np.int32)
+    mcw = np.zeros((S,), dtype=np.float32)
+    abs_sum = np.zeros((S,), dtype=np.float32)
+    rc = lib().fmo_gate(_p(np.ascontiguousarray(x), _u16p), _p(np.ascontiguousarray(wg_eff), _u16p), ctypes.c_int(S),
+                        ctypes.c_int(H), ctypes.c_int(E), ctypes.c_int(k), _p(logits, _f32p), _p(probs, _f32p),
+                        _p(gate_out, _u16p), _p(topk, _i32p), _p(mcw, _f32p), _p(abs_sum, _f32p))
+    if rc != 0:
+        raise RuntimeError(f"fmo_gate failed with code {rc}")
+    slot = np.zeros((S, k), dtype=np.int32)
+    kept = np.zeros((S, k), dtype=np.int32)
+    counts = np.zeros((E,), dtype=np.int32)
+    rc = lib().fmo_slots(_p(topk, _i32p), ctypes.c_int(S), ctypes.c_int(E), ctypes.c_int(k), ctypes.c_int(EC),
+                         _p(slot, _i32p), _p(kept, _i32p), _p(counts, _i32p))
+    if rc != 0:
+        raise RuntimeError(f"fmo_slots failed with code {rc}")
+    gml = np.zeros((E,), dtype=np.float32)
+    gmec = np.zeros((E,), dtype=np.float32)
+    loss = np.zeros((1,), dtype=np.float32)
+    lib().fmo_aux_loss(_p(probs, _f32p), _p(counts, _i32p), ctypes.c_int(S), ctypes.c_int(E), _p(gml, _f32p),
+                       _p(gmec, _f32p), _p(loss, _f32p))
+    return gml, gmec, float(loss[0])
+
+
 def expert_ffn(rows: np.ndarray, w_up: np.ndarray, w_down_eff: np.ndarray, act: int = 0,
                b_up: Optional[np.ndarray] = None, b_down: Optional[np.ndarray] = None):
     """h, y (bf16 bits) for a packet of rows through one expert (Appendix A.6)."""

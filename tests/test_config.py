@@ -63,7 +63,7 @@ def test_missing_required_key_and_missing_file():
         C.load_config("csrc/kleos_config.json")  # the reference's dangling default name
 
 
-@pytest.mark.parametrize("bad", [{"torch_dtype": 1}, {"is_training": 1}, {"expert_top_k": 9, "num_experts": 16}])
+@pytest.mark.parametrize("bad", [{"torch_dtype": 1}, {"is_training": 2}, {"expert_top_k": 9, "num_experts": 16}])
 def test_hot_path_constraints(bad):
     cfg = C.MoEConfig(**{**C.load_config().raw(), **bad})
     with pytest.raises(C.ConfigError):

@@ -272,6 +272,46 @@ def test_misaligned_tensor_is_rejected():
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["small_drop", "E32_k2", "E128_k2"])
+def test_training_mode_aux_loss_matches_oracle(name):
+    """is_training = 1: gML / gMeC / loss accumulated in the router, read back through
+    FM_BUF_AUX_LOSS; two launches with different inputs on one context (the buffers are cleared per launch)."""
+    cfg = CASES[name].replace(is_training=1)
+    ctx = _ctx(cfg)
+    dev = ctx.device
+    for seed in (51, 52):
+        x, wg, we, _, _ = make_inputs(cfg, seed=seed)
+        out = ctx.forward(x.to(dev), wg.to(dev), we.to(dev))
+        ctx.synchronize()
+        aux = ctx.read("aux_loss")
+        gml, gmec, loss = mo.aux_loss(mo.to_bits(x.reshape(cfg.S, cfg.H)),
+                                      mo.gate_weights_effective(mo.to_bits(wg), cfg.E, cfg.H), k=cfg.k, EC=cfg.EC)
+        ref = run_oracle(cfg, x, wg, we)
+        mism = check_topk(ctx.read("topk_idx"), ref)
+        np.testing.assert_allclose(aux[:cfg.E], gml, rtol=2e-5, atol=1e-7)
+        if not mism.any():
+            np.testing.assert_allclose(aux[cfg.E:2 * cfg.E], gmec, rtol=1e-6)
+            np.testing.assert_allclose(aux[2 * cfg.E], loss, rtol=2e-5)
+        check_output(mo.to_bits(out.cpu().reshape(cfg.S, cfg.H)), ref.out, rows_ok=~mism)   # the forward itself is unchanged
+    ctx.close()
+
+
+def test_dense_single_expert_general_path_still_works(monkeypatch):
+    """E = 1 takes the dense fast path by default (no router GEMV, no dispatch copy; test E1_dense above);
+    FM_DENSE_E1=0 sends it through the general router / dispatch path, which must agree too."""
+    monkeypatch.setenv("FM_DENSE_E1", "0")
+    cfg = CASES["E1_dense"]
+    x, wg, we, _, _ = make_inputs(cfg, seed=61)
+    _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
+
+
+def test_dense_single_expert_with_bias_gelu_and_capacity_factor():
+    cfg = MoEConfig(num_experts=1, expert_top_k=1, sequence_len=384, hidden_size=128, intermediate_size=256, hidden_act=1,
+                    capacity_factor=2)
+    x, wg, we, bu, bd = make_inputs(cfg, seed=62, bias=True)
+    _compare(cfg, _run(cfg, x, wg, we, bu, bd), run_oracle(cfg, x, wg, we, bu, bd))
+
+
 def test_reference_style_argument_checks_raise_runtime_error():
     cfg = CASES["tiny"]
     x, wg, we, _, _ = make_inputs(cfg, seed=22)

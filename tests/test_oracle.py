@@ -155,3 +155,20 @@ def test_ambiguity_flags_fire_on_near_ties_only():
     logits = np.array([[1.0, 0.5, 0.49999, -3.0], [1.0, 0.5, 0.0, -3.0]], dtype=np.float32)
     flags = mo.ambiguity_flags(logits, np.array([100.0, 100.0], dtype=np.float32), k=2)
     assert flags.tolist() == [True, False]
+
+
+def test_aux_loss_restatement_against_a_numpy_computation():
+    """is_training = 1: gML = mean_t p[t,e], gMeC = counts[e] / S, loss = sum gML*gMeC / E (gate.cuh:608-635,698-706,763-773)."""
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=256, hidden_size=128, intermediate_size=128)
+    x, wg, we, _, _ = make_inputs(cfg, seed=11)
+    ref = run_oracle(cfg, x, wg, we)
+    gml, gmec, loss = mo.aux_loss(mo.to_bits(x.reshape(cfg.S, cfg.H)), mo.gate_weights_effective(mo.to_bits(wg), cfg.E, cfg.H),
+                                  k=cfg.k, EC=cfg.EC)
+    # independent: library softmax of the oracle's logits in float64
+    l = ref.logits.astype(np.float64)
+    p = np.exp(l - l.max(axis=1, keepdims=True))
+    p /= p.sum(axis=1, keepdims=True)
+    np.testing.assert_allclose(gml, p.mean(axis=0), rtol=1e-5)
+    np.testing.assert_allclose(gmec, ref.counts / cfg.S, rtol=1e-7)
+    np.testing.assert_allclose(loss, float((p.mean(axis=0) * ref.counts / cfg.S).sum() / cfg.E), rtol=1e-5)
+    assert abs(gml.sum() - 1.0) < 1e-5 and abs(gmec.sum() - cfg.k) < 1e-6
