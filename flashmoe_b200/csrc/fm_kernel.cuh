@@ -45,7 +45,8 @@ constexpr int NUM_WARPS = NUM_THREADS / 32;
 constexpr int EPI_WARP0 = 4;   // warps 4..11: warp % 4 selects the TMEM lane quarter, (warp - 4) / 4 the column half
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TMEM_COLS = 512; // two 128x256 fp32 accumulators per CTA (double-buffered against the epilogue)
-constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..12] sub-phase stamps; per tile i < 16 of this CTA (pair):
+constexpr int TRACE_SLOTS = 128; // per CTA: [0..6] phase stamps, [8..14] sub-phase stamps (13 = first tile of a remote packet
+                                 // ready, 14 = all done flags seen); per tile i < 16 of this CTA (pair):
                                  // [16+i] dependencies resolved (scheduler), [32+i] first k-block landed, [48+i] last MMA
                                  // issued (MMA thread), [64+i] accumulator complete (epilogue sees tmem_full), [80+i]
                                  // epilogue stores issued, [96+i] published, [112+i] claimed (scheduler)
@@ -66,7 +67,8 @@ constexpr int BAR_XROWS = BAR_PROD_TAKE + NSCHED;                     // dispatc
 constexpr int BAR_DISP_DONE = BAR_XROWS + 1;                          // this CTA's dispatch no longer uses the stage area
 constexpr int BAR_PUB_FULL = BAR_DISP_DONE + 1;                       // epilogue warps -> publisher: tile's stores issued
 constexpr int BAR_PUB_EMPTY = BAR_PUB_FULL + 2;                       // publisher -> epilogue warps: slot consumed
-constexpr int NUM_BARS = BAR_PUB_EMPTY + 2;                           // 34
+constexpr int BAR_WG = BAR_PUB_EMPTY + 2;                             // router: bulk-staged gate weights
+constexpr int NUM_BARS = BAR_WG + 2;                                  // 36 (one spare keeps the ring 16-byte aligned)
 constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
@@ -241,6 +243,8 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     if (p.aux != nullptr)
         for (int e = tid; e < E; e += NUM_THREADS) aux_s[e] = 0.0f;   // ordered by the block syncs of the first stage below
 
+    uint64_t* wgbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_WG;   // initialised in the kernel prologue
+    uint32_t wgphase = 0;
     const int EG = E < 128 ? E : 128;                      // experts staged per group
     int Hc = (G_WG_BYTES / (EG * 2)) & ~255;               // H columns staged per chunk (multiple of 256)
     if (Hc > H) Hc = H;
@@ -256,9 +260,25 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             for (int hc0 = 0; hc0 < H; hc0 += Hc) {
                 const int hc_len = min(Hc, H - hc0);
                 __syncthreads();  // previous users of wg_s are done (also orders the logit_s zero fill)
+                // stage Wg_eff[eg0 .. eg0+eg_len, hc0 .. hc0+hc_len) -> wg_s[e][Hc] through the TMA engine (1-D bulk copies,
+                // one per expert row, or a single one when the rows are contiguous on both sides): no register round trip,
+                // and the copy runs under the x loads issued below
+                if (warp == 0) {
+                    if (lane == 0) {
+                        fence_proxy_async_all();   // earlier generic accesses to this scratch -> async-proxy writes
+                        mbar_arrive_expect_tx(wgbar, (uint32_t)(eg_len * hc_len * 2));
+                    }
+                    __syncwarp();
+                    if (hc_len == H && Hc == H) {
+                        if (lane == 0) bulk_load_1d(wg_s, p.wg + (size_t)eg0 * H, (uint32_t)(eg_len * H * 2), wgbar);
+                    } else {
+                        for (int e = lane; e < eg_len; e += 32)
+                            bulk_load_1d(wg_s + (size_t)e * Hc, p.wg + (size_t)(eg0 + e) * H + hc0, (uint32_t)(hc_len * 2), wgbar);
+                    }
+                }
                 const bool single = hc_len <= 1024;
                 uint4 xv[4][4];
-                // the first token block's x rows (HBM) are requested BEFORE Wg is staged, so both latencies overlap
+                // the first token block's x rows (HBM) are requested while Wg is in flight, so both latencies overlap
                 if (single && warp * 4 < n_sub) {
                     const int ntk0 = min(4, n_sub - warp * 4);
                     const __nv_bfloat16* xr0 = p.x + (size_t)(t0 + s0 + warp * 4) * H + hc0;
@@ -271,14 +291,8 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                                                                   : make_uint4(0u, 0u, 0u, 0u);
                         }
                 }
-                // stage Wg_eff[eg0 .. eg0+eg_len, hc0 .. hc0+hc_len) -> wg_s[e][Hc], 16 B per thread-iteration
-                const int vec_per_row = hc_len >> 3;
-                for (int i = tid; i < eg_len * vec_per_row; i += NUM_THREADS) {
-                    const int e = i / vec_per_row, v = i - e * vec_per_row;
-                    const uint4 w = ld_global_nc_v4(p.wg + (size_t)(eg0 + e) * H + hc0 + v * 8);
-                    *reinterpret_cast<uint4*>(wg_s + (size_t)e * Hc + v * 8) = w;
-                }
-                __syncthreads();
+                mbar_wait(wgbar, wgphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 902);
+                wgphase ^= 1;
                 // register-blocked GEMV: a warp takes 4 tokens x 8 experts at a time (32 accumulators per lane, one per
                 // (token, expert) pair), lanes split the H columns in 16-byte pieces; all of a step's global loads are
                 // issued before the first FMA, and each staged Wg piece is reused by the 4 tokens.
@@ -343,6 +357,54 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }
         __syncthreads();
         if (tid == 0) trace_stamp(p, 11);
+        if (E <= 32) {
+            // E <= 32: a group of LPT = pow2ceil(E) lanes per token.  Every lane of the group runs the reference's
+            // sequential online-softmax recurrence itself (gate.cuh:575-584; E <= 32 steps on broadcast smem reads, so the
+            // result is bit-identical to the thread-per-row form), then lane `sub` owns expert `sub`: its probability,
+            // the coalesced gateOut store, and its candidate in the k rounds of argmax -- a shuffle reduction that
+            // keeps the larger value and, on equal values, the lower index = the strict-'>' ascending scan of
+            // gate.cuh:654-670.
+            int LPT = 1;
+            while (LPT < E) LPT <<= 1;
+            const int TPW = 32 / LPT, sub = lane & (LPT - 1);
+            for (int tb = warp * TPW; tb < n_sub; tb += NUM_WARPS * TPW) {
+                const int ti_raw = tb + lane / LPT;
+                const bool valid = ti_raw < n_sub;
+                const int ti = valid ? ti_raw : n_sub - 1;
+                const float* l = logit_s + ti * ldl;
+                const int t = t0 + s0 + ti;
+                float dI = 0.0f, mI = -INFINITY;
+                for (int e = 0; e < E; ++e) {
+                    const float pM = mI;
+                    mI = fmaxf(mI, l[e]);
+                    dI = fmaf(dI, fast_expf(pM - mI), fast_expf(l[e] - mI));
+                }
+                const bool own = sub < E;
+                const float pe = own ? __fdividef(fast_expf(l[sub] - mI), dI) : -INFINITY;
+                if (own && valid) p.gate_out[(size_t)t * E + sub] = __float2bfloat16_rn(pe);
+                bool taken = !own;
+                float sum = 0.0f;
+                for (int i = 0; i < k; ++i) {
+                    float bv = taken ? -INFINITY : pe;
+                    int bi = taken ? 0x7fffffff : sub;
+                    for (int off = LPT >> 1; off >= 1; off >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (bi == sub) taken = true;
+                    sum += bv;
+                    if (sub == 0 && valid) {
+                        p.topk_idx[(size_t)t * k + i] = bi;
+                        p.topk_w[(size_t)t * k + i] = __float2bfloat16_rn(bv);
+                        sel_e[(s0 + ti) * k + i] = (int16_t)bi;
+                    }
+                }
+                if (sub == 0 && valid) p.mcw[t] = sum;
+                __syncwarp();
+                if (own && valid) logit_s[ti * ldl + sub] = pe;   // probabilities (training-mode column sums read them)
+            }
+        } else
         // thread-per-token softmax + top-k, the same per-thread recurrence the reference runs after its transpose
         for (int ti = tid; ti < n_sub; ti += NUM_THREADS) {
             float* l = logit_s + ti * ldl;
@@ -399,6 +461,17 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }
     }
     if (tid == 0) trace_stamp(p, 12);
+    // The Wg / logits scratch is free from here on: start staging this chunk's token rows for the dispatch phase now
+    // (one bulk load, same barrier and layout dispatch_phase expects for its first group), so the load runs under the
+    // slot ranks, the grid barrier and the prefix pass instead of after them.
+    if (tid == 0 && n_tok > 0) {
+        const int row_bytes = H * 2;
+        const int rows0 = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
+        uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;
+        fence_proxy_async_all();
+        mbar_arrive_expect_tx(xbar, (uint32_t)(rows0 * row_bytes));
+        bulk_load_1d(smem, p.x + (size_t)t0 * H, (uint32_t)(rows0 * row_bytes), xbar);
+    }
     if (p.aux != nullptr) {   // gML[e] += (sum over this chunk) / S   (gate.cuh:628-634: atomicAdd(gML + e, colAgg / S))
         float* gml = p.aux + (size_t)(p.epoch & 1u) * (2 * E + 1);
         for (int e = tid; e < E; e += NUM_THREADS) atomicAdd(gml + e, __fdividef(aux_s[e], (float)p.S));
@@ -460,12 +533,22 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         const int nb = (int)blockIdx.x * E, n = G * E;
         const bool fixed_e = (E <= DISP_THREADS) && (DISP_THREADS % E) == 0;   // then a thread always meets one e
         int part_b = 0, part_t = 0, cur_e = -1;
-        for (int i = tid; i < n; i += DISP_THREADS) {
-            const int e = i % E;
-            const int v = p.chunk_counts[i];
-            if (i >= nb && i < nb + E) own_s[e] = v;
-            if (fixed_e) { part_t += v; if (i < nb) part_b += v; cur_e = e; }
-            else if (v != 0) { atomicAdd(&total_s[e], v); if (i < nb) atomicAdd(&base_s[e], v); }
+        for (int i0 = tid; i0 < n; i0 += 8 * DISP_THREADS) {
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {   // all loads of the batch are in flight before the first use
+                const int i = i0 + u * DISP_THREADS;
+                v[u] = i < n ? p.chunk_counts[i] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * DISP_THREADS;
+                if (i >= n) break;
+                const int e = i % E;
+                if (i >= nb && i < nb + E) own_s[e] = v[u];
+                if (fixed_e) { part_t += v[u]; if (i < nb) part_b += v[u]; cur_e = e; }
+                else if (v[u] != 0) { atomicAdd(&total_s[e], v[u]); if (i < nb) atomicAdd(&base_s[e], v[u]); }
+            }
         }
         if (cur_e >= 0) {
             if (part_t != 0) atomicAdd(&total_s[cur_e], part_t);
@@ -504,7 +587,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     uint32_t xphase = 0;
     for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
         const int rows = min(rows_per_group, n_tok - g0);
-        if (tid == 0) {
+        if (tid == 0 && g0 > 0) {   // group 0 was requested at the end of the router (gate_phase)
             mbar_arrive_expect_tx(xbar, (uint32_t)(rows * row_bytes));
             bulk_load_1d(x_s, p.x + (size_t)(t0 + g0) * H, (uint32_t)(rows * row_bytes), xbar);
         }
@@ -616,6 +699,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
     const int mstep = PAIR ? 2 : 1;                         // row blocks per work item
     const int tcm_items = (p.TCM + mstep - 1) / mstep;
     int q = 0, qphase = 0, cursor = 0, n = 0;
+    bool seen_remote = false;   // trace only: first tile of a packet from another rank
     for (;;) {
         int kind = -1;
         if (lane == 0) {
@@ -690,6 +774,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 break;
             }
             if (ti.kind >= 0 && n < 16) trace_stamp(p, 16 + n);
+            if (ti.kind >= 0 && ti.src != p.rank && !seen_remote) { seen_remote = true; trace_stamp(p, 13); }
             mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
             ring[q] = ti;
             if (PAIR) {  // mirror the descriptor into the peer CTA's ring over DSMEM, then signal both rings
@@ -768,7 +853,7 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
                     // the partner's producer needs no arrival of its own: it only has to wait for its `empty` slot
                     if (crank == 0) {
                         if (tx) mbar_arrive_expect_tx(&full[stage], 2u * tx); else mbar_arrive(&full[stage]);
-                    } else if (p.dbg_flags & 16) {
+                    } else if (p.dbg_flags & 17) {   // (bit 0: without loads nothing else keeps the partner in lock-step)
                         mbar_arrive_cluster_plain(&full[stage], 0);
                     }
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[stage]), 0);
@@ -1120,7 +1205,7 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
         // arrival counts: full = leader's expect_tx; empty / tmem_full = one tcgen05.commit; tmem_empty = one lane per
         // epilogue warp (of both CTAs); pub_full = one lane per epilogue warp of this CTA; sched_empty = every ring reader
         const int nc = PAIR ? 2 : 1;
-        const int nfull = (PAIR && (p.dbg_flags & 16)) ? 2 : 1;
+        const int nfull = (PAIR && (p.dbg_flags & 17)) ? 2 : 1;
         for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bars[BAR_FULL + i], nfull); mbar_init(&bars[BAR_EMPTY + i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[BAR_TMEM_FULL + i], 1);
@@ -1135,6 +1220,7 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
         }
         mbar_init(&bars[BAR_XROWS], 1);
         mbar_init(&bars[BAR_DISP_DONE], 1);
+        mbar_init(&bars[BAR_WG], 1);
         fence_mbar_init();
     }
     if (warp == 0 && (tid & 31) == 0) {
@@ -1251,6 +1337,7 @@ __device__ __forceinline__ void finish_fused(const FmParams& p, int t0, int n_to
             g.tick(p.dbg, p.timeout_ns, FM_TRAP_RET_FLAG, e, 0xD0E, 0);
     }
     __syncthreads();
+    if (tid == 0) trace_stamp(p, 14);   // every expert's contributions to this rank's tokens are in
     if (p.out_acc != p.out) {
         for (int ti = warp; ti < n_tok; ti += NUM_WARPS) {
             const __nv_bfloat16* src = p.out_acc + (size_t)(t0 + ti) * p.H;

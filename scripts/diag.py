@@ -110,58 +110,7 @@ def stage(args):
             ev1.record(); ctx.synchronize()
             print(f"  phase {nm}: {ev0.elapsed_time(ev1)/n*1e3:.1f} us")
     if st == "trace":
-        out = ctx.forward(xd, wgd, wed); ctx.synchronize()
-        for _ in range(3): ctx.forward(xd, wgd, wed, out=out)
-        ctx.set_trace(True)
-        ctx.forward(xd, wgd, wed, out=out); ctx.synchronize()
-        tr = ctx.read("trace").astype(np.int64)
-        t00 = tr[:, 0].min()
-        names = ["start", "gate", "barrier", "dispatch", "ffn_start", "ffn_end", "combine_end", "", "disp_base", "disp_rows", "", "gate_gemv", "gate_softmax", "t0_kb0_full", "t0_kb4_full", "t0_last_full"]
-        for i, nm in enumerate(names):
-            if not nm: continue
-            v = (tr[:, i] - t00) / 1e3
-            print(f"  {nm:12s} min {v.min():8.1f} med {np.median(v):8.1f} max {v.max():8.1f} us")
-        ready = tr[:, 16:64]; done = tr[:, 64:112]
-        ntiles = (ready > 0).sum(1)
-        print(f"  tiles per CTA min {ntiles.min()} med {np.median(ntiles)} max {ntiles.max()} total {ntiles.sum()}")
-        durs = []; gaps = []
-        for c in range(tr.shape[0]):
-            n = ntiles[c]
-            for i in range(n):
-                prev_done = done[c, i - 1] if i > 0 else tr[c, 4]
-                durs.append((done[c, i] - max(prev_done, ready[c, i])) / 1e3)
-        durs = np.array(durs)
-        print(f"  tile service time (us): min {durs.min():.1f} p10 {np.percentile(durs,10):.1f} med {np.median(durs):.1f} p90 {np.percentile(durs,90):.1f} max {durs.max():.1f}")
-        last_done = np.array([done[c, ntiles[c]-1] if ntiles[c] else tr[c,4] for c in range(tr.shape[0])])
-        v = (last_done - t00) / 1e3
-        print(f"  last tile stored: min {v.min():.1f} med {np.median(v):.1f} max {v.max():.1f} us")
-        claim = tr[:, 112:128]
-        stall = []; gap = []; busy = []; span = []
-        for c in range(tr.shape[0]):
-            n = int(ntiles[c])
-            if n == 0: continue
-            for i in range(min(n, 16)):
-                if claim[c, i] > 0: stall.append((ready[c, i] - claim[c, i]) / 1e3)
-            b = 0.0
-            for i in range(n):
-                prev_done = done[c, i - 1] if i > 0 else tr[c, 4]
-                b += (done[c, i] - max(prev_done, ready[c, i])) / 1e3
-                if i > 0: gap.append(max(0, ready[c, i] - done[c, i - 1]) / 1e3)
-            busy.append(b); span.append((done[c, n - 1] - tr[c, 4]) / 1e3)
-        stall = np.array(stall); gap = np.array(gap); busy = np.array(busy); span = np.array(span)
-        print(f"  claim->ready stall (us): med {np.median(stall):.2f} p90 {np.percentile(stall,90):.2f} max {stall.max():.2f} sum/CTA {stall.sum()/len(busy):.1f}")
-        print(f"  ready after previous tile stored (exposed gap, us): med {np.median(gap):.2f} p90 {np.percentile(gap,90):.2f} max {gap.max():.2f}")
-        print(f"  per-CTA busy med {np.median(busy):.1f} span med {np.median(span):.1f} max {span.max():.1f}; sum busy / (max span * CTAs) = {busy.sum()/(span.max()*len(busy)):.3f}")
-        k0 = [ (done[c,i]-max(done[c,i-1] if i>0 else tr[c,4], ready[c,i]))/1e3 for c in range(tr.shape[0]) for i in range(int(ntiles[c]))]
-        k0 = np.array(k0); short = k0[k0 < 15]; long_ = k0[k0 >= 15]
-        if len(short) and len(long_): print(f"  short tiles n={len(short)} mean {short.mean():.2f} us; long tiles n={len(long_)} mean {long_.mean():.2f} us")
-        ep = tr[:, 120:125]
-        if (ep[:, 0] > 0).any():
-            m = ep[:, 0] > 0
-            d = (ep[m, 1:] - ep[m, :1]) / 1e3
-            print("  epilogue of tile #2 (us after tmem_full): chunk0 %.2f drain_all %.2f barrier %.2f published %.2f" % tuple(np.median(d, axis=0)))
-            print("  tile #2: ready->tmem_full %.2f us (med)" % np.median((ep[m, 0] - ready[m, 2]) / 1e3))
-        np.save("gpurun_out/trace_%s.npy" % args.cfg, tr)
+        print("  the per-tile timeline lives in scripts/trace_gantt.py (single GPU) and scripts/trace_multi.py (torchrun)")
     ctx.close()
 
 
@@ -171,7 +120,7 @@ if __name__ == "__main__":
     ap.add_argument("--noscale", action="store_true"); ap.add_argument("--all-experts", dest="all_experts", action="store_true")
     args = ap.parse_args()
     if args.stage == "all":
-        for st in ("gate", "ffn", "combine", "full", "time", "trace"):
+        for st in ("gate", "ffn", "combine", "full", "time"):
             print(f"===== stage {st} ({args.cfg}) =====", flush=True)
             cmd = [sys.executable, __file__, "--cfg", args.cfg, "--stage", st] + (["--noscale"] if args.noscale else [])
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
