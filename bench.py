@@ -172,6 +172,19 @@ class ClockSampler:
                 "sampler_errors": self.errors}
 
 
+def in_tree_native_libs():
+    """In-tree shared objects mapped into this process (what the driver records as `native_so_loaded`)."""
+    libs = set()
+    try:
+        for line in open("/proc/self/maps"):
+            path = line.rsplit(" ", 1)[-1].strip()
+            if path.startswith(ROOT) and ".so" in os.path.basename(path):
+                libs.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(libs)
+
+
 def usable_cpus() -> int:
     """Host threads this process may really use: CPU affinity capped by the cgroup CPU quota (the GPU box shows 128
     CPUs but grants a quota of ~24; running MKL with 128 threads there is 5x slower than with 24-32)."""
@@ -230,7 +243,7 @@ def run_reference_arm(args, rank, world):
                     "(oracle/torch_moe.py) on the host cores",
             "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "native_so_mapped": in_tree_native_libs()}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -485,7 +498,7 @@ def main():
         "run": {"token_expert_pairs_executed": res["rows_total"], "output_buffer": res["out_buffer"],
                 "l2": "no explicit flush: the per-step working set (expert weights + activations/staging, >= 250 MB per "
                       "rank for config B) exceeds the 126 MB L2"},
-        "roofline": roof, "gpu_launches": res["launches"], "clocks": res["clocks"],
+        "roofline": roof, "gpu_launches": res["launches"], "clocks": res["clocks"], "native_so_mapped": in_tree_native_libs(),
     }
     if "e2e_ms" in res:
         line["e2e"] = {"value": world * S / (res["e2e_ms"] * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": S * cfg.H * 2,

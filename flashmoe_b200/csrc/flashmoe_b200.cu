@@ -490,34 +490,45 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     ctx->TN1 = ceil_div(d.H, ctx->bn1);
     ctx->num_pkts = world * nLx;
 
-    // work-item blocks: own rank's packets first, then rank+1, ...; GEMM1 lags GEMM0 by one packet
-    std::vector<int> order;
-    for (int j = 0; j < world; ++j) {
-        const int src = (rank + j) % world;
-        for (int le = 0; le < nLx; ++le) order.push_back(src * nLx + le);
+    // Work list.  Sources in the order own rank, rank+1, ... (local rows need no NVLink hop, so they are ready first).
+    // With CTA pairs a work item is a 256-row tile made of two 128-row halves that share the B operand (same local expert):
+    //   * world even: halves = the SAME row block of the packets of two different source ranks ("cross-source pairing":
+    //     no half is wasted when a packet has an odd number of row blocks -- with 128 experts on 8 GPUs every packet
+    //     has exactly one);
+    //   * otherwise:  halves = two consecutive row blocks of one packet.
+    // All GEMM0 blocks first, then the GEMM1 blocks (measured best on config B; FM_G1_LAG interleaves them with a lag).
+    const bool xpair = ctx->pair && world >= 2 && (world % 2) == 0 && env_int("FM_XPAIR", 1) != 0;
+    struct Unit { int pkt, pkt2; };
+    std::vector<Unit> units;
+    if (xpair) {
+        for (int j = 0; j < world; j += 2)
+            for (int le = 0; le < nLx; ++le)
+                units.push_back({((rank + j) % world) * nLx + le, ((rank + j + 1) % world) * nLx + le});
+    } else {
+        for (int j = 0; j < world; ++j)
+            for (int le = 0; le < nLx; ++le) units.push_back({((rank + j) % world) * nLx + le, -1});
     }
     std::vector<fm::TileBlock> blocks;
     int start = 0;
-    auto push = [&](int kind, int pkt) {
+    auto push = [&](int kind, const Unit& u) {
         fm::TileBlock b;
-        b.kind = kind; b.pkt = pkt; b.start = start; b.pad = 0;
+        b.kind = kind; b.pkt = u.pkt; b.start = start; b.pkt2 = u.pkt2;
         blocks.push_back(b);
-        const int row_items = ctx->pair ? (d.TCM + 1) / 2 : d.TCM;  // a pair covers two 128-row blocks per item
+        const int row_items = (ctx->pair && u.pkt2 < 0) ? (d.TCM + 1) / 2 : d.TCM;
         start += row_items * (kind == 0 ? ctx->TN0 : ctx->TN1);
     };
-    // GEMM1 of a packet is queued `lag` packets after its GEMM0 so the h row blocks it needs are complete when claimed
-    // (default: all GEMM0 blocks first -- measured best on config B: 163 us vs 168 us with a lag of 2)
-    int lag = env_int("FM_G1_LAG", (int)order.size());
+    // GEMM1 of a unit is queued `lag` units after its GEMM0 so the h row blocks it needs are complete when claimed
+    int lag = env_int("FM_G1_LAG", (int)units.size());
     if (lag < 1) lag = 1;
-    for (size_t i = 0; i < order.size(); ++i) {
-        push(0, order[i]);
-        if ((int)i >= lag) push(1, order[i - lag]);
+    for (size_t i = 0; i < units.size(); ++i) {
+        push(0, units[i]);
+        if ((int)i >= lag) push(1, units[i - lag]);
     }
-    for (size_t i = order.size() > (size_t)lag ? order.size() - lag : 0; i < order.size(); ++i) push(1, order[i]);
+    for (size_t i = units.size() > (size_t)lag ? units.size() - lag : 0; i < units.size(); ++i) push(1, units[i]);
     ctx->num_blocks = (int)blocks.size();
     ctx->total_items = start;
     fm::TileBlock sentinel;
-    sentinel.kind = -1; sentinel.pkt = 0; sentinel.start = start; sentinel.pad = 0;
+    sentinel.kind = -1; sentinel.pkt = 0; sentinel.start = start; sentinel.pkt2 = -1;
     blocks.push_back(sentinel);
 
 #define FM_TRY(expr)          \

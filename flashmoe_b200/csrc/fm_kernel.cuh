@@ -95,11 +95,12 @@ constexpr int G_OFF_BASE = 131072 + 49152;  // int32 base[E] + total[E] + own[E]
 constexpr int G_XROWS_BYTES = 131072;       // dispatch: staged token rows (reuses the Wg / logits scratch)
 static_assert(G_OFF_BASE + 12288 <= OFF_EPI, "gate scratch must fit in the stage area");
 
-struct TileBlock {  // one contiguous run of work items: all tiles of one GEMM of one packet
+struct TileBlock {  // one contiguous run of work items: all tiles of one GEMM of one packet (or of a packet pair)
     int kind;       // 0 = GEMM0 (x.W_up^T), 1 = GEMM1 (h.W_down^T)
     int pkt;        // local packet index = src * nLx + le
     int start;      // first global item id of this block
-    int pad;
+    int pkt2;       // CTA pairs: -1 = the pair's second 128-row half is the NEXT row block of `pkt`; >= 0 = it is the SAME
+                    // row block of packet pkt2 (same local expert, another source rank) -- see the host's work list
 };
 
 struct FmParams {
@@ -657,20 +658,19 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
 //   superset: row blocks beyond the packet's row count are skipped once the packet flag is known.  A GEMM1 tile waits for
 //   g0_done[pkt][m] == TN0 (both row blocks of the pair).
 // ============================================================================================================
-struct TileInfo {     // 64 bytes, written by the (leader's) scheduler warp, read by producer / MMA / epilogue warps
+struct TileInfo {     // 64 bytes, written by the (leader's) scheduler warp, read by producer / MMA / epilogue / publisher warps.
+                      // Per-half fields are indexed by the CTA's rank in the pair (solo CTAs use index 0).
     int kind;         // 0 GEMM0, 1 GEMM1, -1 stop
-    int pkt;          // local packet index src * nLx + le
-    int mblk;         // row block of cluster rank 0 (rank 1 of a pair works on mblk + 1)
     int ntile;
-    int rows[2];      // valid rows of the row block of cluster rank 0 / 1
-    int src;
-    int le;
+    int le;           // local expert (both halves share it: same B operand)
     int bn;           // tile width
     int nk;           // k-blocks
-    int a_row;        // TMA row coordinate of rank 0's A tile (rank 1: + 128)
     int b_row;        // TMA row coordinate of the B tile (rank 1 of a pair: + bn/2)
-    int cnt;          // rows of the whole packet
-    int pad[3];
+    int pkt[2];       // local packet index src * nLx + le of each half
+    int mblk[2];      // 128-row block of that packet
+    int rows[2];      // valid rows of that block (0 = this half is idle)
+    int src[2];       // source rank of the packet
+    int cnt[2];       // rows of the whole packet
 };
 static_assert(sizeof(TileInfo) == 64, "TileInfo must be 4 x 16 bytes");
 
@@ -696,8 +696,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
     uint64_t* prod_take = bars + BAR_PROD_TAKE;
     TileInfo* ring = reinterpret_cast<TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
-    const int mstep = PAIR ? 2 : 1;                         // row blocks per work item
-    const int tcm_items = (p.TCM + mstep - 1) / mstep;
+    const int nh = PAIR ? 2 : 1;                            // 128-row halves per work item
     int q = 0, qphase = 0, cursor = 0, n = 0;
     bool seen_remote = false;   // trace only: first tile of a packet from another rank
     for (;;) {
@@ -708,8 +707,9 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 mbar_wait(&prod_take[pq], ((n - 1) / NSCHED) & 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, 200 + pq);
             }
             TileInfo ti;
-            ti.kind = -1; ti.pkt = 0; ti.mblk = 0; ti.ntile = 0; ti.rows[0] = 0; ti.rows[1] = 0; ti.src = 0; ti.le = 0;
-            ti.bn = 0; ti.nk = 0; ti.a_row = 0; ti.b_row = 0; ti.cnt = 0; ti.pad[0] = ti.pad[1] = ti.pad[2] = 0;
+            ti.kind = -1; ti.ntile = 0; ti.le = 0; ti.bn = 0; ti.nk = 0; ti.b_row = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) { ti.pkt[h] = 0; ti.mblk[h] = 0; ti.rows[h] = 0; ti.src[h] = 0; ti.cnt[h] = 0; }
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
@@ -717,64 +717,75 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 while (id >= p.blocks[cursor + 1].start) ++cursor;
                 const TileBlock blk = p.blocks[cursor];
                 const int local = id - blk.start;
-                const int mblk = (local % tcm_items) * mstep, nt = local / tcm_items;
-                const int src = blk.pkt / p.nLx, le = blk.pkt - src * p.nLx;
-                // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
-                unsigned long long f = ((unsigned long long)p.epoch << 32) | (unsigned int)p.S;   // dense: all S rows, in x
-                bool stale = false;
-                if (!p.dense) {
+                // item -> (row block(s), column tile); row blocks fastest.  Within-packet pairing: halves = row blocks
+                // 2m, 2m+1 of one packet.  Cross-source pairing (pkt2 >= 0): halves = row block m of two packets.
+                const bool cross = PAIR && blk.pkt2 >= 0;
+                const int m_items = (PAIR && !cross) ? (p.TCM + 1) / 2 : p.TCM;
+                const int m = local % m_items, nt = local / m_items;
+                const int le = blk.pkt % p.nLx;
+                bool any = false;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h >= nh) break;
+                    const int pkt = (h == 1 && cross) ? blk.pkt2 : blk.pkt;
+                    const int mb = cross ? m : (PAIR ? 2 * m + h : m);
+                    const int src = pkt / p.nLx;
+                    ti.pkt[h] = pkt; ti.mblk[h] = mb; ti.src[h] = src; ti.rows[h] = 0; ti.cnt[h] = 0;
+                    if (mb >= p.TCM) continue;
+                    // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
+                    unsigned long long f = ((unsigned long long)p.epoch << 32) | (unsigned int)p.S;   // dense: all S rows, in x
+                    bool stale = false;
+                    if (!p.dense && !(h == 1 && !cross)) {   // (within-packet pairing: the second half shares the flag)
+                        SpinGuard g;
+                        for (;;) {
+                            f = ld_acquire_sys_u64(p.recv_flag + pkt);
+                            const int ahead = (int)((unsigned int)(f >> 32) - p.epoch);
+                            if (ahead == 0) break;
+                            // The source rank is already in a LATER forward: it only gets there after every real tile of
+                            // this packet has been returned to it, so whatever item of the static superset is left here
+                            // is an empty row block.
+                            if (ahead > 0) { stale = true; break; }
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, pkt, (unsigned int)(f >> 32), p.epoch);
+                        }
+                    } else if (h == 1 && !cross) {
+                        if (ti.cnt[0] == 0 && ti.rows[0] == 0 && !any) stale = true;   // first half found the packet empty / stale
+                        f = ((unsigned long long)p.epoch << 32) | (unsigned int)ti.cnt[0];
+                    }
+                    if (stale) continue;
+                    const int cnt = (int)(f & 0xffffffffull);
+                    ti.cnt[h] = cnt;
+                    if (h == 0 || cross) {   // once per packet and GEMM (its first item): bookkeeping that needs the count
+                        if (local == 0 && blk.kind == 0 && !p.dense) p.recv_cnt[pkt] = cnt;
+                        if (p.fused && local == 0 && blk.kind == 1 && cnt == 0)   // nothing to contribute: tell the source now
+                            st_release_sys_u64(p.peer_done_flag[src] + (size_t)(p.rank * p.nLx + le),
+                                               (unsigned long long)p.epoch << 32);
+                    }
+                    const int rows = max(0, min(BLOCK_M, cnt - mb * BLOCK_M));
+                    ti.rows[h] = rows;
+                    if (rows == 0) continue;   // empty row block of the static superset
+                    any = true;
                     SpinGuard g;
-                    for (;;) {
-                        f = ld_acquire_sys_u64(p.recv_flag + blk.pkt);
-                        const int ahead = (int)((unsigned int)(f >> 32) - p.epoch);
-                        if (ahead == 0) break;
-                        // The source rank is already in a LATER forward: it only gets there after every real tile of
-                        // this packet has been returned to it, so whatever item of the static superset is left here
-                        // is an empty row block.
-                        if (ahead > 0) { stale = true; break; }
-                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, blk.pkt, (unsigned int)(f >> 32), p.epoch);
-                    }
-                }
-                if (stale) continue;
-                const int cnt = (int)(f & 0xffffffffull);
-                if (local == 0 && blk.kind == 0 && !p.dense) p.recv_cnt[blk.pkt] = cnt;
-                if (p.fused && local == 0 && blk.kind == 1 && cnt == 0)   // nothing to contribute: tell the source now
-                    st_release_sys_u64(p.peer_done_flag[src] + (size_t)(p.rank * p.nLx + le),
-                                       (unsigned long long)p.epoch << 32);
-                if (mblk * BLOCK_M >= cnt) continue;  // empty row block(s) of the static superset
-                const int rows0 = min(BLOCK_M, cnt - mblk * BLOCK_M);
-                const int rows1 = PAIR ? max(0, min(BLOCK_M, cnt - (mblk + 1) * BLOCK_M)) : 0;
-                if (blk.kind == 1) {  // GEMM1 needs whole h row blocks (reference notifyNext, processor.cuh:490-615)
-                    for (int r = 0; r < mstep; ++r) {
-                        if (r == 1 && rows1 == 0) break;
-                        SpinGuard g;
-                        const unsigned int* ctr = p.g0_done + (size_t)blk.pkt * p.TCM + mblk + r;
+                    if (blk.kind == 1) {  // GEMM1 needs the whole h row block (reference notifyNext, processor.cuh:490-615)
+                        const unsigned int* ctr = p.g0_done + (size_t)pkt * p.TCM + mb;
                         while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
-                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, blk.pkt, mblk + r, 0);
-                    }
-                } else if ((p.phase_mask & 1u) && !p.dense) {  // GEMM0 needs its row blocks of the packet to have landed (dispatch acks)
-                    for (int r = 0; r < mstep; ++r) {
-                        const int need = r == 0 ? rows0 : rows1;
-                        if (need == 0) break;
-                        SpinGuard g;
-                        const unsigned int* ctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + blk.pkt) * p.TCM + mblk + r;
-                        while (ld_acquire_sys_u32(ctr) < (unsigned int)need)
-                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, blk.pkt, mblk + r, need);
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, pkt, mb, 0);
+                    } else if ((p.phase_mask & 1u) && !p.dense) {  // GEMM0 needs the rows of this block to have landed (dispatch acks)
+                        const unsigned int* ctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + pkt) * p.TCM + mb;
+                        while (ld_acquire_sys_u32(ctr) < (unsigned int)rows)
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, pkt, mb, rows);
                     }
                 }
-                ti.kind = blk.kind; ti.pkt = blk.pkt; ti.mblk = mblk; ti.ntile = nt;
-                ti.rows[0] = rows0; ti.rows[1] = rows1;
-                ti.src = src; ti.le = le; ti.cnt = cnt;
+                if (!any) continue;
+                ti.kind = blk.kind; ti.ntile = nt; ti.le = le;
                 ti.bn = p.bn[blk.kind];
                 ti.nk = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
-                ti.a_row = blk.pkt * p.pEC + mblk * BLOCK_M;
                 // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
                 // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
                 ti.b_row = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * ti.bn;
                 break;
             }
             if (ti.kind >= 0 && n < 16) trace_stamp(p, 16 + n);
-            if (ti.kind >= 0 && ti.src != p.rank && !seen_remote) { seen_remote = true; trace_stamp(p, 13); }
+            if (ti.kind >= 0 && (ti.src[0] != p.rank || (PAIR && ti.src[1] != p.rank)) && !seen_remote) { seen_remote = true; trace_stamp(p, 13); }
             mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
             ring[q] = ti;
             if (PAIR) {  // mirror the descriptor into the peer CTA's ring over DSMEM, then signal both rings
@@ -828,7 +839,8 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
             const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
             const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
             const int b_rows = ti.bn / PC::B_ROWS_DIV;
-            const int a_row = ti.a_row + (PAIR ? (int)crank * BLOCK_M : 0);
+            const int hh = PAIR ? (int)crank : 0;
+            const int a_row = ti.pkt[hh] * p.pEC + ti.mblk[hh] * BLOCK_M;
             const int b_row = ti.b_row + (PAIR ? (int)crank * b_rows : 0);
             const int take_at = min(ti.nk - 1, max(0, ti.nk - p.claim_ahead_kb));
             const int pf = p.prefetch_kb;
@@ -1050,18 +1062,18 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         if (ti.kind < 0) break;
         const int N = ti.kind == 0 ? p.P : p.H;
         const int n0 = ti.ntile * ti.bn;
-        const int my_rows = ti.rows[PAIR ? crank : 0];
-        const int my_mblk = ti.mblk + (PAIR ? (int)crank : 0);
+        const int hh = PAIR ? (int)crank : 0;
+        const int my_rows = ti.rows[hh], my_mblk = ti.mblk[hh], my_pkt = ti.pkt[hh], my_src = ti.src[hh];
         const __nv_bfloat16* bias = ti.kind == 0 ? (p.b_up ? p.b_up + (size_t)ti.le * p.P : nullptr)
                                                  : (p.b_down ? p.b_down + (size_t)ti.le * p.H : nullptr);
         // destination rows: GEMM0 -> local h staging; GEMM1 -> the SOURCE rank's return buffer (peer store),
         // like the reference's GEMM1 epilogue writing into the peer heap (packet.cuh:338-340, processor.cuh:713-720)
         __nv_bfloat16* out_rows;
         if (ti.kind == 0) {
-            out_rows = p.hidden + ((size_t)ti.pkt * p.pEC + (size_t)my_mblk * BLOCK_M) * p.P;
+            out_rows = p.hidden + ((size_t)my_pkt * p.pEC + (size_t)my_mblk * BLOCK_M) * p.P;
         } else {
             const int e_global = p.rank * p.nLx + ti.le;
-            out_rows = p.peer_ret_y[ti.src] + ((size_t)e_global * p.pEC + (size_t)my_mblk * BLOCK_M) * p.H;
+            out_rows = p.peer_ret_y[my_src] + ((size_t)e_global * p.pEC + (size_t)my_mblk * BLOCK_M) * p.H;
         }
         // 64-column chunks of the tile that exist (N is a multiple of 64, not necessarily of the tile width), split
         // between the two warps of this lane quarter
@@ -1075,12 +1087,12 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         if (fuse && p.dense) {
             my_tok = my_mblk * BLOCK_M + quarter * 32 + lane;   // row i of the only packet IS token i
         } else if (fuse && quarter * 32 + lane < my_rows) {
-            const uint4 m = ld_global_v4(p.recv_meta + (size_t)ti.pkt * p.pEC + (size_t)my_mblk * BLOCK_M + quarter * 32 + lane);
+            const uint4 m = ld_global_v4(p.recv_meta + (size_t)my_pkt * p.pEC + (size_t)my_mblk * BLOCK_M + quarter * 32 + lane);
             my_tok = (int)m.x;
             my_pw = __uint_as_float(m.y);
             my_mcw = __uint_as_float(m.z);
         }
-        __nv_bfloat16* acc_base = fuse ? p.peer_out_acc[ti.src] : nullptr;
+        __nv_bfloat16* acc_base = fuse ? p.peer_out_acc[my_src] : nullptr;
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
@@ -1155,30 +1167,29 @@ __device__ __forceinline__ void ffn_publisher(const FmParams& p, uint8_t* smem, 
             release_to_leader<PAIR>(&sched_empty[q], crank);
             kind = ti.kind;
             if (kind >= 0) {
-                const int my_rows = ti.rows[PAIR ? crank : 0];
-                const int my_mblk = ti.mblk + (PAIR ? (int)crank : 0);
+                const int hh = PAIR ? (int)crank : 0;
+                const int my_rows = ti.rows[hh], my_mblk = ti.mblk[hh], my_pkt = ti.pkt[hh], my_src = ti.src[hh];
                 mbar_wait(&pub_full[ps], pphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_PUB, 10 + ps);
                 mbar_arrive(&pub_empty[ps]);
                 if (my_rows > 0) {
                     if (kind == 0) {
                         fence_proxy_async_global();
-                        red_release_gpu_add_u32(p.g0_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                        red_release_gpu_add_u32(p.g0_done + (size_t)my_pkt * p.TCM + my_mblk, 1u);
                     } else if (p.fused) {
                         fence_acq_rel_sys();   // this tile's adds are performed before the packet counter moves
-                        const unsigned int old = atom_acq_rel_gpu_add_u32(p.pkt_done + ti.pkt, 1u);
-                        const unsigned int want = (unsigned int)(((ti.cnt + BLOCK_M - 1) / BLOCK_M) * p.TN1);
+                        const unsigned int old = atom_acq_rel_gpu_add_u32(p.pkt_done + my_pkt, 1u);
+                        const unsigned int want = (unsigned int)(((ti.cnt[hh] + BLOCK_M - 1) / BLOCK_M) * p.TN1);
                         if (old + 1u == want) {   // every GEMM1 tile of packet (src, le) has been added into src's output
-                            fence_acq_rel_sys();
-                            st_release_sys_u64(p.peer_done_flag[ti.src] + (size_t)(p.rank * p.nLx + ti.le),
+                            st_release_sys_u64(p.peer_done_flag[my_src] + (size_t)(p.rank * p.nLx + ti.le),
                                                (unsigned long long)p.epoch << 32);
                         }
                     } else {
                         fence_acq_rel_sys();
-                        const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)ti.pkt * p.TCM + my_mblk, 1u);
+                        const unsigned int old = atom_acq_rel_gpu_add_u32(p.g1_done + (size_t)my_pkt * p.TCM + my_mblk, 1u);
                         if (old == (unsigned int)p.TN1 - 1u) {  // whole rows of this block are on the source rank
                             fence_acq_rel_sys();
                             const int e_global = p.rank * p.nLx + ti.le;
-                            st_release_sys_u64(p.peer_ret_flag[ti.src] + (size_t)e_global * p.TCM + my_mblk,
+                            st_release_sys_u64(p.peer_ret_flag[my_src] + (size_t)e_global * p.TCM + my_mblk,
                                                ((unsigned long long)p.epoch << 32) | (unsigned int)my_rows);
                         }
                     }

@@ -80,7 +80,13 @@ class MoEContext:
     """Owns the native context (workspaces, symmetric slab, peer mappings) for one rank."""
 
     def __init__(self, cfg: Optional[MoEConfig] = None, rank: int = 0, world: int = 1,
-                 device: Optional[int] = None, group=None, timeout_ms: Optional[int] = None):
+                 device: Optional[int] = None, group=None, timeout_ms: Optional[int] = None,
+                 symmetric: Optional[str] = None):
+        """`symmetric` selects how the peers' slabs are mapped when world > 1: "ipc" (default; cudaMalloc + CUDA IPC
+        handles over torch.distributed) or "torch" (the slab is allocated with torch.distributed._symmetric_memory --
+        the allocator PyTorch backs with CUDA VMM / NVSHMEM -- and the peer pointers come from its rendezvous; this is
+        the hook for externally managed symmetric heaps, reference bootstrap.cuh:359-360,442-443).  Environment
+        override: FM_SYMM=ipc|torch."""
         self._L = _lib.load()
         self._ctx = ctypes.c_void_p()
         if device is None:
@@ -96,8 +102,15 @@ class MoEContext:
         self.cfg = cfg if cfg is not None else _lib.compiled_config()
         if timeout_ms is not None:
             _lib.check(self._L.fm_set_timeout_ms(self._ctx, int(timeout_ms)))
+        self.symmetric = (symmetric or os.environ.get("FM_SYMM") or "ipc").lower()
+        self._symm_tensor = None   # keeps an externally allocated slab alive
         if world > 1:
-            self._attach_peers(group)
+            if self.symmetric == "ipc":
+                self._attach_peers(group)
+            elif self.symmetric == "torch":
+                self._attach_torch_symmetric_memory(group)
+            else:
+                raise ValueError(f"symmetric must be 'ipc' or 'torch', got {self.symmetric!r}")
 
     # ------------------------------------------------------------------ peers
     def _attach_peers(self, group) -> None:
@@ -112,6 +125,31 @@ class MoEContext:
         _lib.check(self._L.fm_symm_attach_ipc(self._ctx, blob))
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)  # every rank's slab is mapped (and zeroed) before anyone dispatches into it
+
+    def _attach_torch_symmetric_memory(self, group) -> None:
+        """Externally allocated symmetric slab: torch.distributed._symmetric_memory.empty + rendezvous give every rank a
+        same-sized allocation and the peers' mapped base pointers; the library adopts them through
+        fm_symm_use_external + fm_symm_attach_ptrs (no cudaMalloc / CUDA IPC of its own)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        nbytes = ctypes.c_size_t()
+        _lib.check(self._L.fm_symm_size(self._ctx, ctypes.byref(nbytes)))
+        n = (nbytes.value + 1023) // 1024 * 1024
+        t = symm_mem.empty(n, dtype=torch.uint8, device=self.device)
+        t.zero_()
+        if t.data_ptr() % 1024:
+            raise RuntimeError("symmetric memory allocation is not 1 KiB aligned")
+        hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or ptrs[self.rank] != t.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory rendezvous result")
+        _lib.check(self._L.fm_symm_use_external(self._ctx, t.data_ptr(), n))
+        arr = (ctypes.c_void_p * self.world)(*ptrs)
+        _lib.check(self._L.fm_symm_attach_ptrs(self._ctx, arr))
+        self._symm_tensor, self._symm_handle = t, hdl
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
 
     # ------------------------------------------------------------------ hot path
     @property

@@ -28,6 +28,22 @@ def test_reference_arm_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "tokens" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the same `config` object as the GPU arm prints (the driver compares the two arms' configs) ...
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.config_dict("B", bench.BASELINE_CONFIGS["B"], 1)
+    # ... and the product's native library is never mapped into the reference arm's process
+    assert d["native_so_mapped"] == [] or all("flashmoe" not in s for s in d["native_so_mapped"]), d["native_so_mapped"]
+
+
+def test_every_baseline_config_is_selectable():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert set(bench.BASELINE_CONFIGS) >= {"A", "B", "C", "D1k", "D4k", "D16k", "D64k", "E8", "E16", "E32", "E64", "E128"}
+    for name, cfg in bench.BASELINE_CONFIGS.items():
+        assert bench.config_dict(name, cfg, 8)["workload"].startswith("configs[")
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
