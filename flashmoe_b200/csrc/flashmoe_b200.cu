@@ -102,7 +102,7 @@ struct fm_ctx {
     int grid = 0;
     int tpc = 0;
     int TN0 = 0, TN1 = 0, num_pkts = 0, num_blocks = 0, total_items = 0;
-    int bn0 = 256, bn1 = 256, claim_ahead_kb = 8;
+    int bn0 = 256, bn1 = 256, claim_ahead_kb = 16;
     int dbg_flags = 0;
     bool coop = true;    // cooperative launch attribute (validates co-residency of the persistent grid)
     int prefetch_kb = 0;
@@ -144,6 +144,11 @@ struct fm_ctx {
     bool dense = false;   // E == 1: GEMM0 reads x in place, no router GEMV, no dispatch copy (reference fffn.cuh:31-167)
     float* aux = nullptr; // is_training: [2][2E+1] {gML, gMeC, loss} by epoch parity
     const void* cached_x = nullptr;
+    int* recv_tok = nullptr;            // [nLx, pEC] slot -> token of the local packets (TMA gather4 source rows)
+    unsigned int* tok_rows = nullptr;   // [2, nLx, TCM]
+    bool gather = false;
+    const void* cached_xg = nullptr;
+    CUtensorMap tm_xg;
     unsigned int* pkt_done = nullptr;
     void* peer_base[FM_MAX_WORLD] = {};
     bool peer_opened[FM_MAX_WORLD] = {};
@@ -265,6 +270,10 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
         if ((rc = make_tmap(&c->tm_a0, x, (uint64_t)d.S, d.H, fm::BLOCK_M))) return rc;
         c->cached_x = x;
     }
+    if (c->gather && c->cached_xg != x) {   // x as [S, H] with a {64, 1} box: rows are picked one by one (TMA gather4)
+        if ((rc = make_tmap(&c->tm_xg, x, (uint64_t)d.S, d.H, 1))) return rc;
+        c->cached_xg = x;
+    }
     if (!c->tm_static_ready) {
         if (!c->dense && (rc = make_tmap(&c->tm_a0, static_cast<char*>(c->symm) + c->off_recv_x, (uint64_t)c->num_pkts * d.pEC, d.H,
                                          fm::BLOCK_M)))
@@ -286,6 +295,7 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     fm::FmParams p;
     memset(&p, 0, sizeof(p));
     p.tm_a0 = c->tm_a0; p.tm_b0 = c->tm_b0; p.tm_a1 = c->tm_a1; p.tm_b1 = c->tm_b1;
+    if (c->gather) p.tm_xg = c->tm_xg;
     p.S = d.S; p.H = d.H; p.P = d.P; p.E = d.E; p.k = d.k; p.W = d.world; p.rank = d.rank; p.nLx = nLx;
     p.EC = d.EC; p.pEC = d.pEC; p.TCM = d.TCM; p.act = c->cfg.hidden_act;
     p.TN0 = c->TN0; p.TN1 = c->TN1; p.tpc = c->tpc; p.num_pkts = c->num_pkts; p.num_blocks = c->num_blocks;
@@ -326,6 +336,9 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     if (d.world == 1) p.peer_out_acc[0] = p.out;
     p.aux = c->aux;
     p.dense = c->dense ? 1 : 0;
+    p.gather = c->gather ? 1 : 0;
+    p.recv_tok = c->recv_tok;
+    p.tok_rows = c->tok_rows;
     p.dbg = c->dbg_dev;
     p.trace = c->trace_on ? c->trace : nullptr;
 
@@ -443,6 +456,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         const char* f = getenv("FM_FUSED_COMBINE");
         ctx->fused = ((f != nullptr && *f) ? atoi(f) != 0 : true) && d.k <= 2;
         ctx->dense = d.E == 1 && world == 1 && env_int("FM_DENSE_E1", 1) != 0;
+        ctx->gather = !ctx->dense && env_int("FM_GATHER", 1) != 0;
         if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
         ctx->d.grid = ctx->grid;
     }
@@ -454,7 +468,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     const int nLx = d.num_local_experts;
     ctx->bn0 = env_int("FM_BN0", 256) == 128 ? 128 : 256;
     ctx->bn1 = env_int("FM_BN1", 256) == 128 ? 128 : 256;
-    ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 8);
+    ctx->claim_ahead_kb = env_int("FM_CLAIM_AHEAD_KB", 16);   // measured on config B: 8 -> 144.5 us, 12 -> 142.3, 14 -> 140.6
     ctx->dbg_flags = env_int("FM_DBG_FLAGS", 0);
     // The persistent grid spins on flags, counters and one grid barrier, so every CTA must be resident: the launch is
     // cooperative (the driver then refuses to start it unless the whole grid fits, also next to other work on the GPU).
@@ -565,6 +579,10 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     FM_TRY(dev_alloc(&ctx->hidden, (size_t)ctx->num_pkts * d.pEC * d.P));
     FM_TRY(dev_alloc(&ctx->trace, (size_t)ctx->grid * fm::TRACE_SLOTS));
     if (c.is_training) FM_TRY(dev_alloc(&ctx->aux, (size_t)2 * (2 * d.E + 1)));
+    if (ctx->gather) {
+        FM_TRY(dev_alloc(&ctx->recv_tok, (size_t)nLx * d.pEC));
+        FM_TRY(dev_alloc(&ctx->tok_rows, (size_t)2 * nLx * d.TCM));
+    }
 
     // symmetric slab: [recv_x | ret_y | recv_flag | ret_flag]  (reference heap + flags, bootstrap.cuh:348-362)
     size_t off = 0;
@@ -611,7 +629,7 @@ FM_API int fm_destroy(fm_ctx_t* ctx) {
         if (ctx->peer_opened[r] && ctx->peer_base[r] != nullptr) cudaIpcCloseMemHandle(ctx->peer_base[r]);
     void* bufs[] = {ctx->topk_idx, ctx->topk_w, ctx->mcw, ctx->slot, ctx->counts, ctx->gate_out, ctx->chunk_counts,
                     ctx->ctrl, ctx->g0_done, ctx->g1_done, ctx->pkt_done, ctx->recv_cnt, ctx->blocks, ctx->hidden, ctx->trace,
-                    ctx->aux};
+                    ctx->aux, ctx->recv_tok, ctx->tok_rows};
     for (void* b : bufs)
         if (b != nullptr) cudaFree(b);
     for (int i = 0; i < FM_HOST_SLOTS; ++i) {

@@ -108,6 +108,7 @@ struct FmParams {
     CUtensorMap tm_b0;  // expert_weights as [nLx*2*P, H]  box {64, 256}  (W_up rows)
     CUtensorMap tm_a1;  // hidden  as [W*nLx*pEC, P]  box {64, 128}
     CUtensorMap tm_b1;  // expert_weights as [nLx*2*H, P]  box {64, 256}  (W_down rows)
+    CUtensorMap tm_xg;  // x as [S, H], box {64, 1}: TMA gather4 of token rows for local packets (no dispatch copy needed)
     int S, H, P, E, k, W, rank, nLx, EC, pEC, TCM, act;
     int TN0, TN1, tpc, num_pkts, num_blocks, total_items;
     int bn[2];          // tile width of GEMM0 / GEMM1 (128 or 256)
@@ -157,6 +158,11 @@ struct FmParams {
     __nv_bfloat16* peer_out_acc[FM_MAX_WORLD];
     // training mode (is_training = 1): [2][2E+1] f32 by epoch parity = {gML[E] mean gate probability per expert,
     // gMeC[E] mean routed fraction per expert, loss} (reference moe/gate.cuh:608-635,698-706,763-773); nullptr otherwise
+    // local packets (source = this rank): token of every slot, acknowledged BEFORE the row copies, so a GEMM0 tile
+    // claimed early can gather its A rows straight from x (TMA gather4) instead of waiting for the copies to land
+    int* recv_tok;             // [nLx, pEC] (local packets only, indexed by local expert)
+    unsigned int* tok_rows;    // [2, nLx, TCM] rows of block b whose token entry is written, by epoch parity
+    int gather;                // 0 = off
     float* aux;
     int dense;          // E == 1: no router GEMV, no dispatch copy; GEMM0 reads x in place (reference moe/fffn.cuh:31-167)
     DebugRecord* dbg;
@@ -266,7 +272,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 // and the copy runs under the x loads issued below
                 if (warp == 0) {
                     if (lane == 0) {
-                        fence_proxy_async_all();   // earlier generic accesses to this scratch -> async-proxy writes
+                        fence_proxy_async_smem();   // earlier generic accesses to this scratch -> async-proxy writes
                         mbar_arrive_expect_tx(wgbar, (uint32_t)(eg_len * hc_len * 2));
                     }
                     __syncwarp();
@@ -465,11 +471,11 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     // The Wg / logits scratch is free from here on: start staging this chunk's token rows for the dispatch phase now
     // (one bulk load, same barrier and layout dispatch_phase expects for its first group), so the load runs under the
     // slot ranks, the grid barrier and the prefix pass instead of after them.
-    if (tid == 0 && n_tok > 0) {
+    if (tid == 32 && n_tok > 0) {   // (warp 1: warp 0 is about to compute the slot ranks)
         const int row_bytes = H * 2;
         const int rows0 = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
         uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;
-        fence_proxy_async_all();
+        fence_proxy_async_smem();
         mbar_arrive_expect_tx(xbar, (uint32_t)(rows0 * row_bytes));
         bulk_load_1d(smem, p.x + (size_t)t0 * H, (uint32_t)(rows0 * row_bytes), xbar);
     }
@@ -578,6 +584,31 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             atomicAdd(a + 2 * E, __fdividef(me * ce, (float)E));
         }
     }
+    // Local packets first get their token table (slot -> token) and an acknowledgement of it: a GEMM0 tile claimed before
+    // the row copies below have landed gathers its rows from x by these indices (ffn_producer, TMA gather4).
+    const unsigned int par = p.epoch & 1u;
+    if (p.gather) {
+        const int first_local = p.rank * p.nLx;
+        for (int i = tid; i < n_tok * k; i += DISP_THREADS) {
+            const int e = sel_e[i];
+            const int le = e - first_local;
+            if (le >= 0 && le < p.nLx) {
+                const int s = base_s[e] + rank_s[i];
+                if (s < p.EC) p.recv_tok[(size_t)le * p.pEC + s] = t0 + i / k;
+            }
+        }
+        disp_sync();
+        for (int le = tid; le < p.nLx; le += DISP_THREADS) {
+            const int e = first_local + le;
+            const int lo = base_s[e];
+            const int hi = min(lo + own_s[e], p.EC);
+            if (hi > lo) {
+                unsigned int* ctr = p.tok_rows + ((size_t)par * p.nLx + le) * p.TCM;
+                for (int b = lo / BLOCK_M; b <= (hi - 1) / BLOCK_M; ++b)
+                    red_release_gpu_add_u32(ctr + b, (unsigned int)(min(hi, (b + 1) * BLOCK_M) - max(lo, b * BLOCK_M)));
+            }
+        }
+    }
     // Row copies through the TMA engine: the chunk's token rows are contiguous in x, so one bulk load stages up to
     // 128 KiB of them in shared memory and every kept (token, pick) pair is one bulk store of a whole row into the
     // owner rank's receive buffer (peer-mapped over NVLink).  No per-lane load/store latency chains.
@@ -632,7 +663,6 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     if (tid == 0) trace_stamp(p, 9);
     // acknowledge: this chunk's rows of expert e occupy slots [base, base + own) of packet (me, e), cut at EC.  The
     // release covers every dispatch thread's completed row / record stores (observed through the barrier above).
-    const unsigned int par = p.epoch & 1u;
     for (int e = tid; e < E; e += DISP_THREADS) {
         const int lo = base_s[e];
         const int hi = min(lo + own_s[e], p.EC);
@@ -663,9 +693,8 @@ struct TileInfo {     // 64 bytes, written by the (leader's) scheduler warp, rea
     int kind;         // 0 GEMM0, 1 GEMM1, -1 stop
     int ntile;
     int le;           // local expert (both halves share it: same B operand)
-    int bn;           // tile width
-    int nk;           // k-blocks
     int b_row;        // TMA row coordinate of the B tile (rank 1 of a pair: + bn/2)
+    int gather[2];    // GEMM0, local packet: 1 = this half's A rows are gathered from x (its row copies had not landed yet)
     int pkt[2];       // local packet index src * nLx + le of each half
     int mblk[2];      // 128-row block of that packet
     int rows[2];      // valid rows of that block (0 = this half is idle)
@@ -699,6 +728,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
     const int nh = PAIR ? 2 : 1;                            // 128-row halves per work item
     int q = 0, qphase = 0, cursor = 0, n = 0;
     bool seen_remote = false;   // trace only: first tile of a packet from another rank
+    bool warmed = false;
     for (;;) {
         int kind = -1;
         if (lane == 0) {
@@ -707,9 +737,9 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 mbar_wait(&prod_take[pq], ((n - 1) / NSCHED) & 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, 200 + pq);
             }
             TileInfo ti;
-            ti.kind = -1; ti.ntile = 0; ti.le = 0; ti.bn = 0; ti.nk = 0; ti.b_row = 0;
+            ti.kind = -1; ti.ntile = 0; ti.le = 0; ti.b_row = 0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) { ti.pkt[h] = 0; ti.mblk[h] = 0; ti.rows[h] = 0; ti.src[h] = 0; ti.cnt[h] = 0; }
+            for (int h = 0; h < 2; ++h) { ti.pkt[h] = 0; ti.mblk[h] = 0; ti.rows[h] = 0; ti.src[h] = 0; ti.cnt[h] = 0; ti.gather[h] = 0; }
             for (;;) {
                 const int id = (int)atomicAdd(p.claim, 1u);
                 if (id >= p.total_items) break;
@@ -723,6 +753,17 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 const int m_items = (PAIR && !cross) ? (p.TCM + 1) / 2 : p.TCM;
                 const int m = local % m_items, nt = local / m_items;
                 const int le = blk.pkt % p.nLx;
+                if (n == 0 && !warmed) {
+                    // the pair's very first tile: its weight tile comes from HBM (first touch) -- ask for it to be brought
+                    // into L2 now, while the rows this tile needs are still being dispatched
+                    warmed = true;
+                    const CUtensorMap* tb = blk.kind == 0 ? &p.tm_b0 : &p.tm_b1;
+                    const int bn_w = p.bn[blk.kind], nk_w = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
+                    const int b0 = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * bn_w;
+                    const int step = PAIR ? bn_w / 2 : bn_w;
+                    for (int kb = 0; kb < min(nk_w, 32); ++kb)
+                        for (int r = 0; r < bn_w; r += step) tma_prefetch_l2_2d(tb, kb * BLOCK_K, b0 + r);
+                }
                 bool any = false;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -730,7 +771,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                     const int pkt = (h == 1 && cross) ? blk.pkt2 : blk.pkt;
                     const int mb = cross ? m : (PAIR ? 2 * m + h : m);
                     const int src = pkt / p.nLx;
-                    ti.pkt[h] = pkt; ti.mblk[h] = mb; ti.src[h] = src; ti.rows[h] = 0; ti.cnt[h] = 0;
+                    ti.pkt[h] = pkt; ti.mblk[h] = mb; ti.src[h] = src; ti.rows[h] = 0; ti.cnt[h] = 0; ti.gather[h] = 0;
                     if (mb >= p.TCM) continue;
                     // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
                     unsigned long long f = ((unsigned long long)p.epoch << 32) | (unsigned int)p.S;   // dense: all S rows, in x
@@ -771,17 +812,23 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                             g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, pkt, mb, 0);
                     } else if ((p.phase_mask & 1u) && !p.dense) {  // GEMM0 needs the rows of this block to have landed (dispatch acks)
                         const unsigned int* ctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + pkt) * p.TCM + mb;
-                        while (ld_acquire_sys_u32(ctr) < (unsigned int)rows)
+                        // local packet: the token table of the block is acknowledged before its row copies -- if it is
+                        // complete while the rows are not, the producer gathers the rows from x itself
+                        const unsigned int* tctr = (p.gather && src == p.rank)
+                            ? p.tok_rows + ((size_t)(p.epoch & 1u) * p.nLx + le) * p.TCM + mb : nullptr;
+                        for (;;) {
+                            if (ld_acquire_sys_u32(ctr) >= (unsigned int)rows) break;
+                            if (tctr != nullptr && ld_acquire_gpu_u32(tctr) >= (unsigned int)rows) { ti.gather[h] = 1; break; }
                             g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, pkt, mb, rows);
+                        }
                     }
                 }
                 if (!any) continue;
                 ti.kind = blk.kind; ti.ntile = nt; ti.le = le;
-                ti.bn = p.bn[blk.kind];
-                ti.nk = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
+                const int bn_item = p.bn[blk.kind];
                 // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
                 // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
-                ti.b_row = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * ti.bn;
+                ti.b_row = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * bn_item;
                 break;
             }
             if (ti.kind >= 0 && n < 16) trace_stamp(p, 16 + n);
@@ -821,44 +868,69 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
     int stage = 0, phase = 0, q = 0, qphase = 0;
     bool first = true;
     for (;;) {
-        int kind = -1;
+        int kind = -1, gather = 0, g_base = 0, g_rows = 0;
         TileInfo ti;
         if (lane == 0) {
             wait_sched_full<PAIR>(p, &sched_full[q], qphase, 300 + q);
             ti = ring[q];
             release_to_leader<PAIR>(&sched_empty[q], crank);
             kind = ti.kind;
+            const int hh0 = PAIR ? (int)crank : 0;
+            gather = ti.gather[hh0];
+            g_base = ti.le * p.pEC + ti.mblk[hh0] * BLOCK_M;   // this half's first slot in the local token table
+            g_rows = ti.rows[hh0];
         }
         kind = __shfl_sync(0xffffffffu, kind, 0);
         if (kind < 0) break;
+        gather = __shfl_sync(0xffffffffu, gather, 0);
+        // gather mode (GEMM0 tile of a local packet whose row copies have not landed): every lane owns four rows of the
+        // A tile and fetches them from x by token index, k-block by k-block (cp.async.bulk.tensor ... tile::gather4)
+        int4 tok = make_int4(0, 0, 0, 0);
+        if (gather) {
+            g_base = __shfl_sync(0xffffffffu, g_base, 0);
+            g_rows = __shfl_sync(0xffffffffu, g_rows, 0);
+            if (lane * 4 < g_rows) tok = ld_global_cg_i4(p.recv_tok + g_base + lane * 4);
+            if (lane * 4 + 1 >= g_rows) tok.y = 0;   // padding rows of the last block: any valid row (results are dropped)
+            if (lane * 4 + 2 >= g_rows) tok.z = 0;
+            if (lane * 4 + 3 >= g_rows) tok.w = 0;
+        }
+        int nk = 0;
         if (lane == 0) {
             if (first && (p.phase_mask & 1u) && !(p.dbg_flags & 32))   // the stage area doubles as the dispatch staging buffer
                 mbar_wait(&bars[BAR_DISP_DONE], 0, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, 901);
             first = false;
             fence_proxy_async_global();  // rows written by generic-proxy stores (peers / other SMs) -> TMA reads
-            const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
-            const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
-            const int b_rows = ti.bn / PC::B_ROWS_DIV;
+            nk = (kind == 0 ? p.H : p.P) / BLOCK_K;
+        }
+        nk = __shfl_sync(0xffffffffu, nk, 0);
+        const CUtensorMap* ta = kind == 0 ? &p.tm_a0 : &p.tm_a1;
+        const CUtensorMap* tb = kind == 0 ? &p.tm_b0 : &p.tm_b1;
+        const int b_rows = p.bn[kind] / PC::B_ROWS_DIV;
+        const int take_at = min(nk - 1, max(0, nk - p.claim_ahead_kb));
+        int a_row = 0, b_row = 0;
+        if (lane == 0) {
             const int hh = PAIR ? (int)crank : 0;
-            const int a_row = ti.pkt[hh] * p.pEC + ti.mblk[hh] * BLOCK_M;
-            const int b_row = ti.b_row + (PAIR ? (int)crank * b_rows : 0);
-            const int take_at = min(ti.nk - 1, max(0, ti.nk - p.claim_ahead_kb));
+            a_row = ti.pkt[hh] * p.pEC + ti.mblk[hh] * BLOCK_M;
+            b_row = ti.b_row + (PAIR ? (int)crank * b_rows : 0);
             const int pf = p.prefetch_kb;
             if (pf > 0) {   // warm L2 for the k-blocks just beyond the smem pipeline
-                for (int kb = PC::STAGES; kb < min(ti.nk, PC::STAGES + pf); ++kb) {
+                for (int kb = PC::STAGES; kb < min(nk, PC::STAGES + pf); ++kb) {
                     tma_prefetch_l2_2d(ta, kb * BLOCK_K, a_row);
                     tma_prefetch_l2_2d(tb, kb * BLOCK_K, b_row);
                 }
             }
-            for (int kb = 0; kb < ti.nk; ++kb) {
-                if (pf > 0 && kb + PC::STAGES + pf < ti.nk) {
+        }
+        for (int kb = 0; kb < nk; ++kb) {
+            uint8_t* sa = smem + stage * PC::STAGE_BYTES;
+            const bool ld_a = (p.dbg_flags & 5) == 0, ld_b = (p.dbg_flags & 9) == 0;   // experiments only
+            if (lane == 0) {
+                const int pf = p.prefetch_kb;
+                if (pf > 0 && kb + PC::STAGES + pf < nk) {
                     tma_prefetch_l2_2d(ta, (kb + PC::STAGES + pf) * BLOCK_K, a_row);
                     tma_prefetch_l2_2d(tb, (kb + PC::STAGES + pf) * BLOCK_K, b_row);
                 }
                 if (kb == take_at && crank == 0) mbar_arrive(&prod_take[q]);  // lets the scheduler claim the next tile
                 mbar_wait(&empty[stage], phase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, stage);
-                uint8_t* sa = smem + stage * PC::STAGE_BYTES;
-                const bool ld_a = (p.dbg_flags & 5) == 0, ld_b = (p.dbg_flags & 9) == 0;   // experiments only
                 const uint32_t tx = (ld_a ? (uint32_t)A_STAGE_BYTES : 0u) + (ld_b ? (uint32_t)(b_rows * BLOCK_K * 2) : 0u);
                 if (PAIR) {
                     // the leader's expect_tx covers both CTAs' bytes (every completion is credited to ITS barrier), so
@@ -869,15 +941,23 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
                         mbar_arrive_cluster_plain(&full[stage], 0);
                     }
                     const uint32_t leader_full = mapa_shared(smem_u32(&full[stage]), 0);
-                    if (ld_a) tma_load_2d_pair(sa, ta, kb * BLOCK_K, a_row, leader_full);
+                    if (ld_a && !gather) tma_load_2d_pair(sa, ta, kb * BLOCK_K, a_row, leader_full);
                     if (ld_b) tma_load_2d_pair(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, leader_full);
                 } else {
                     if (tx) mbar_arrive_expect_tx(&full[stage], tx); else mbar_arrive(&full[stage]);
-                    if (ld_a) tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
+                    if (ld_a && !gather) tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
                     if (ld_b) tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
                 }
-                if (++stage == PC::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (gather) {   // warp-uniform
+                __syncwarp();   // lane 0 has seen the stage empty
+                if (ld_a) {
+                    if (PAIR) tma_gather4_pair(sa + lane * 512, &p.tm_xg, kb * BLOCK_K, tok.x, tok.y, tok.z, tok.w,
+                                               mapa_shared(smem_u32(&full[stage]), 0));
+                    else tma_gather4(sa + lane * 512, &p.tm_xg, kb * BLOCK_K, tok.x, tok.y, tok.z, tok.w, &full[stage]);
+                }
+            }
+            if (++stage == PC::STAGES) { stage = 0; phase ^= 1; }
         }
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         __syncwarp();
@@ -902,8 +982,8 @@ __device__ __forceinline__ void ffn_mma(const FmParams& p, uint8_t* smem, uint64
         if (lane == 0) {
             mbar_wait(&sched_full[q], qphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_FULL, q);
             kind = ring[q].kind;
-            nk = ring[q].nk;
-            bn = ring[q].bn;
+            nk = kind < 0 ? 0 : (kind == 0 ? p.H : p.P) / BLOCK_K;
+            bn = kind < 0 ? BLOCK_N : p.bn[kind];
             mbar_arrive(&sched_empty[q]);
         }
         kind = __shfl_sync(0xffffffffu, kind, 0);
@@ -1061,7 +1141,8 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         if (ti.kind < 0) break;
         const int N = ti.kind == 0 ? p.P : p.H;
-        const int n0 = ti.ntile * ti.bn;
+        const int bn = p.bn[ti.kind];
+        const int n0 = ti.ntile * bn;
         const int hh = PAIR ? (int)crank : 0;
         const int my_rows = ti.rows[hh], my_mblk = ti.mblk[hh], my_pkt = ti.pkt[hh], my_src = ti.src[hh];
         const __nv_bfloat16* bias = ti.kind == 0 ? (p.b_up ? p.b_up + (size_t)ti.le * p.P : nullptr)
@@ -1077,8 +1158,8 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
         }
         // 64-column chunks of the tile that exist (N is a multiple of 64, not necessarily of the tile width), split
         // between the two warps of this lane quarter
-        const int per_half = ti.bn / 128;
-        const int nvalid = my_rows > 0 ? min(ti.bn / 64, (N - n0) / 64) : 0;
+        const int per_half = bn / 128;
+        const int nvalid = my_rows > 0 ? min(bn / 64, (N - n0) / 64) : 0;
         const int c0 = min(chalf * per_half, nvalid), c1 = min(c0 + per_half, nvalid);
         // fused GEMM1 -> combine: this thread owns accumulator row (quarter*32 + lane); fetch that row's routing record
         const bool fuse = p.fused != 0 && ti.kind == 1;
@@ -1438,6 +1519,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
             // peer can write them yet (a rank starts forward epoch+1 only after this launch has returned all its rows)
             unsigned int* next_rows = p.recv_rows + (size_t)((p.epoch + 1u) & 1u) * p.num_pkts * p.TCM;
             for (int i = tid; i < p.num_pkts * p.TCM; i += NUM_THREADS) next_rows[i] = 0u;
+            if (p.gather) {
+                unsigned int* next_tok = p.tok_rows + (size_t)((p.epoch + 1u) & 1u) * p.nLx * p.TCM;
+                for (int i = tid; i < p.nLx * p.TCM; i += NUM_THREADS) next_tok[i] = 0u;
+            }
             if (p.aux != nullptr) {   // the loss buffers of the next launch (reference clearState, moe.cuh:49-54)
                 float* next_aux = p.aux + (size_t)((p.epoch + 1u) & 1u) * (2 * p.E + 1);
                 for (int i = tid; i < 2 * p.E + 1; i += NUM_THREADS) next_aux[i] = 0.0f;

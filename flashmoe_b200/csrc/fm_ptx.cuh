@@ -185,6 +185,11 @@ __device__ __forceinline__ uint4 ld_global_v4(const void* p) {  // coherent path
                  : "memory");
     return v;
 }
+__device__ __forceinline__ int4 ld_global_cg_i4(const void* p) {   // L2-coherent (data written by other SMs in this launch)
+    int4 v;
+    asm volatile("ld.global.cg.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_global_v4(void* p, const uint4& v) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                  : "memory");
@@ -220,6 +225,9 @@ __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bul
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared-memory only: generic-proxy accesses to smem <-> async-proxy (TMA) accesses to the same smem; does not wait for
+// the thread's outstanding global stores
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // L2 prefetch of a tensor tile (no smem destination, no barrier): hides HBM latency for k-blocks the pipeline will
 // request a few steps later
@@ -340,6 +348,26 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+// TMA gather: four arbitrary rows (r0..r3) of a 2-D tensor, `box` columns starting at column c0, land as four
+// consecutive 128-byte rows at smem_dst (tensor map encoded with box {64, 1}, 128-byte swizzle -- the swizzle is a
+// function of the shared-memory address, so a 512-byte aligned destination inside a tile keeps the tile's layout).
+__device__ __forceinline__ void tma_gather4(void* smem_dst, const void* tmap, int32_t c0, int32_t r0, int32_t r1, int32_t r2,
+                                            int32_t r3, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::1 "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+        : "memory");
+}
+// CTA-pair form: issued by either CTA, completion bytes credited to the barrier at `bar_cluster_addr` (the leader's copy)
+__device__ __forceinline__ void tma_gather4_pair(void* smem_dst, const void* tmap, int32_t c0, int32_t r0, int32_t r1,
+                                                 int32_t r2, int32_t r3, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.cta_group::2 "
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // same warp id in both CTAs

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+echo "=== pytest gpu parity (gather on)"; timeout 1200 python -m pytest tests/test_gpu_parity.py tests/test_zz_gpu_large_shapes.py -x -q -m gpu 2>&1 | tail -8
+echo "=== pcie"; timeout 120 python scripts/pcie_probe.py 2>&1 | tail -6
+F='^===|landed->acc|per k-block|per pair|gate_done|disp_prefix|dispatch_end|ffn_end|kernel_end|barrier|gate_topk|gate_gemv|disp_rows'
+echo "=== gantt gather on"; timeout 300 python scripts/trace_gantt.py --cfg B --label gather 2>&1 | grep -E "$F"
+echo "=== gantt gather off"; FM_GATHER=0 timeout 300 python scripts/trace_gantt.py --cfg B --label nogather 2>&1 | grep -E "$F"
+for ca in 16 24 32; do echo "=== claim ahead $ca"; FM_CLAIM_AHEAD_KB=$ca timeout 300 python scripts/trace_gantt.py --cfg B --label ca$ca 2>&1 | grep -E "^===|per pair"; done
+echo "=== bench B"; timeout 600 python bench.py --steps 200 --warmup 32 2>&1 | tail -1 | tee gpurun_out/r2_bench_b2.json | cut -c1-300
