@@ -456,7 +456,10 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         const char* f = getenv("FM_FUSED_COMBINE");
         ctx->fused = ((f != nullptr && *f) ? atoi(f) != 0 : true) && d.k <= 2;
         ctx->dense = d.E == 1 && world == 1 && env_int("FM_DENSE_E1", 1) != 0;
-        ctx->gather = !ctx->dense && env_int("FM_GATHER", 1) != 0;
+        // TMA gather4 of local rows for tiles claimed before their copies landed: correct, but off by default -- measured on
+        // config B a gather tile takes 24 us instead of 6.6 (32 gather4 operations per k-block per CTA sustain only about
+        // one per 90 clocks), which costs far more than the ~5 us earlier start buys (160 vs 144 us per forward)
+        ctx->gather = !ctx->dense && env_int("FM_GATHER", 0) != 0;
         if (ctx->pair && (ctx->grid & 1)) ctx->grid -= 1;  // CTA pairs need an even grid
         ctx->d.grid = ctx->grid;
     }

@@ -250,6 +250,15 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     if (p.aux != nullptr)
         for (int e = tid; e < E; e += NUM_THREADS) aux_s[e] = 0.0f;   // ordered by the block syncs of the first stage below
 
+    if (p.fused) {
+        // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output, moe.cuh:43-48).
+        // Done first: the stores drain under the router's load latencies, long before anybody can add into these rows
+        // (an expert only sees a token after this CTA's dispatch acknowledgement, which is ordered behind these stores).
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const int vec_per_row = H >> 3;
+        for (int i = tid; i < n_tok * vec_per_row; i += NUM_THREADS)
+            st_global_v4(p.out_acc + (size_t)t0 * H + (size_t)i * 8, z);
+    }
     uint64_t* wgbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_WG;   // initialised in the kernel prologue
     uint32_t wgphase = 0;
     const int EG = E < 128 ? E : 128;                      // experts staged per group
@@ -623,12 +632,6 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             mbar_arrive_expect_tx(xbar, (uint32_t)(rows * row_bytes));
             bulk_load_1d(x_s, p.x + (size_t)(t0 + g0) * H, (uint32_t)(rows * row_bytes), xbar);
         }
-        if (g0 == 0 && p.fused) {   // while the rows are in flight: the accumulation target rows start at zero
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);   // (reference clearState zeroes the output, moe.cuh:43-48)
-            const int vec_per_row = H >> 3;
-            for (int i = tid; i < n_tok * vec_per_row; i += DISP_THREADS)
-                st_global_v4(p.out_acc + (size_t)t0 * H + (size_t)i * 8, z);
-        }
         mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 900);
         xphase ^= 1;
         for (int i = tid; i < rows * k; i += DISP_THREADS) {
@@ -671,7 +674,8 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             unsigned int* ctr = p.peer_recv_rows[owner] + ((size_t)par * p.num_pkts + (size_t)(p.rank * p.nLx + le)) * p.TCM;
             for (int b = lo / BLOCK_M; b <= (hi - 1) / BLOCK_M; ++b) {
                 const int n = min(hi, (b + 1) * BLOCK_M) - max(lo, b * BLOCK_M);
-                red_release_sys_add_u32(ctr + b, (unsigned int)n);
+                if (owner == p.rank) red_release_gpu_add_u32(ctr + b, (unsigned int)n);   // same GPU: the cheaper fence
+                else red_release_sys_add_u32(ctr + b, (unsigned int)n);
             }
         }
     }
@@ -728,7 +732,6 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
     const int nh = PAIR ? 2 : 1;                            // 128-row halves per work item
     int q = 0, qphase = 0, cursor = 0, n = 0;
     bool seen_remote = false;   // trace only: first tile of a packet from another rank
-    bool warmed = false;
     for (;;) {
         int kind = -1;
         if (lane == 0) {
@@ -753,17 +756,6 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 const int m_items = (PAIR && !cross) ? (p.TCM + 1) / 2 : p.TCM;
                 const int m = local % m_items, nt = local / m_items;
                 const int le = blk.pkt % p.nLx;
-                if (n == 0 && !warmed) {
-                    // the pair's very first tile: its weight tile comes from HBM (first touch) -- ask for it to be brought
-                    // into L2 now, while the rows this tile needs are still being dispatched
-                    warmed = true;
-                    const CUtensorMap* tb = blk.kind == 0 ? &p.tm_b0 : &p.tm_b1;
-                    const int bn_w = p.bn[blk.kind], nk_w = (blk.kind == 0 ? p.H : p.P) / BLOCK_K;
-                    const int b0 = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * bn_w;
-                    const int step = PAIR ? bn_w / 2 : bn_w;
-                    for (int kb = 0; kb < min(nk_w, 32); ++kb)
-                        for (int r = 0; r < bn_w; r += step) tma_prefetch_l2_2d(tb, kb * BLOCK_K, b0 + r);
-                }
                 bool any = false;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -810,6 +802,13 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                         const unsigned int* ctr = p.g0_done + (size_t)pkt * p.TCM + mb;
                         while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
                             g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, pkt, mb, 0);
+                        if (p.gather && p.fused && src == p.rank && (p.phase_mask & 1u)) {
+                            // the block's GEMM0 tiles may all have run in gather mode, i.e. before its row copies and
+                            // routing records landed: the combine epilogue reads those records, so order behind their ack
+                            const unsigned int* rctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + pkt) * p.TCM + mb;
+                            while (ld_acquire_sys_u32(rctr) < (unsigned int)rows)
+                                g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, pkt, mb, rows);
+                        }
                     } else if ((p.phase_mask & 1u) && !p.dense) {  // GEMM0 needs the rows of this block to have landed (dispatch acks)
                         const unsigned int* ctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + pkt) * p.TCM + mb;
                         // local packet: the token table of the block is acknowledged before its row copies -- if it is
@@ -1318,6 +1317,26 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
     if (warp == 0 && (tid & 31) == 0) {
         tma_prefetch_desc(&p.tm_a0); tma_prefetch_desc(&p.tm_b0);
         tma_prefetch_desc(&p.tm_a1); tma_prefetch_desc(&p.tm_b1);
+    }
+    if (warp == 3 && (tid & 31) == 0 && (p.phase_mask & 3u) == 3u && (!PAIR || (blockIdx.x & 1) == 0)) {
+        // Warm L2 with the weight tile this pair will most likely claim first (item id = pair index: the first wave is
+        // claimed in arrival order), pipeline depth only: HBM is idle during the router and the first tile's loads are
+        // then L2 hits.  A wrong guess costs nothing -- the tile is needed by some pair of the first wave anyway.
+        const int id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+        if (id < p.total_items) {
+            int cur = 0;
+            while (id >= p.blocks[cur + 1].start) ++cur;
+            const TileBlock blk = p.blocks[cur];
+            const int local = id - blk.start;
+            const bool cross = PAIR && blk.pkt2 >= 0;
+            const int m_items = (PAIR && !cross) ? (p.TCM + 1) / 2 : p.TCM;
+            const int nt = local / m_items, le = blk.pkt % p.nLx, bn_w = p.bn[blk.kind];
+            const CUtensorMap* tb = blk.kind == 0 ? &p.tm_b0 : &p.tm_b1;
+            const int b0 = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * bn_w;
+            const int nk_w = (blk.kind == 0 ? p.H : p.P) / BLOCK_K, step = PAIR ? bn_w / 2 : bn_w;
+            for (int kb = 0; kb < min(nk_w, PipeCfg<PAIR>::STAGES); ++kb)
+                for (int r = 0; r < bn_w; r += step) tma_prefetch_l2_2d(tb, kb * BLOCK_K, b0 + r);
+        }
     }
     if (warp == 2 && (p.phase_mask & 2u)) { if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
     tcgen05_fence_before();
