@@ -514,16 +514,18 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     //     has exactly one);
     //   * otherwise:  halves = two consecutive row blocks of one packet.
     // All GEMM0 blocks first, then the GEMM1 blocks (measured best on config B; FM_G1_LAG interleaves them with a lag).
-    const bool xpair = ctx->pair && world >= 2 && (world % 2) == 0 && env_int("FM_XPAIR", 1) != 0;
-    struct Unit { int pkt, pkt2; };
+    // Cross-source pairing only pays when a packet has an ODD number of row blocks (otherwise pairing inside the packet
+    // wastes nothing and keeps the local packets -- whose rows are ready first -- free of any remote dependency).
+    const bool xpair = ctx->pair && world >= 2 && (world % 2) == 0 && (d.TCM % 2) == 1 && env_int("FM_XPAIR", 1) != 0;
+    struct Unit { int pkt, pkt2; bool local; };
     std::vector<Unit> units;
     if (xpair) {
         for (int j = 0; j < world; j += 2)
             for (int le = 0; le < nLx; ++le)
-                units.push_back({((rank + j) % world) * nLx + le, ((rank + j + 1) % world) * nLx + le});
+                units.push_back({((rank + j) % world) * nLx + le, ((rank + j + 1) % world) * nLx + le, j == 0});
     } else {
         for (int j = 0; j < world; ++j)
-            for (int le = 0; le < nLx; ++le) units.push_back({((rank + j) % world) * nLx + le, -1});
+            for (int le = 0; le < nLx; ++le) units.push_back({((rank + j) % world) * nLx + le, -1, j == 0});
     }
     std::vector<fm::TileBlock> blocks;
     int start = 0;
@@ -534,14 +536,25 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         const int row_items = (ctx->pair && u.pkt2 < 0) ? (d.TCM + 1) / 2 : d.TCM;
         start += row_items * (kind == 0 ? ctx->TN0 : ctx->TN1);
     };
-    // GEMM1 of a unit is queued `lag` units after its GEMM0 so the h row blocks it needs are complete when claimed
+    // GEMM0: local sources first (their rows are acknowledged first), then rank+1, rank+2, ...  GEMM1: REMOTE sources
+    // first, local last -- the outputs of remote packets cross NVLink as reductions and their done flags have a link round
+    // trip ahead of them, so they should not be what every rank finishes with; the local packets' adds are cheap and
+    // nobody but this rank waits for them.  FM_G1_LAG interleaves GEMM1 of a unit `lag` units after its GEMM0 instead.
+    std::vector<Unit> g1_units;
+    for (const Unit& u : units) if (!u.local) g1_units.push_back(u);
+    for (const Unit& u : units) if (u.local) g1_units.push_back(u);
     int lag = env_int("FM_G1_LAG", (int)units.size());
     if (lag < 1) lag = 1;
-    for (size_t i = 0; i < units.size(); ++i) {
-        push(0, units[i]);
-        if ((int)i >= lag) push(1, units[i - lag]);
+    if (lag >= (int)units.size()) {
+        for (const Unit& u : units) push(0, u);
+        for (const Unit& u : g1_units) push(1, u);
+    } else {
+        for (size_t i = 0; i < units.size(); ++i) {
+            push(0, units[i]);
+            if ((int)i >= lag) push(1, units[i - lag]);
+        }
+        for (size_t i = units.size() - lag; i < units.size(); ++i) push(1, units[i]);
     }
-    for (size_t i = units.size() > (size_t)lag ? units.size() - lag : 0; i < units.size(); ++i) push(1, units[i]);
     ctx->num_blocks = (int)blocks.size();
     ctx->total_items = start;
     fm::TileBlock sentinel;

@@ -250,15 +250,6 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     if (p.aux != nullptr)
         for (int e = tid; e < E; e += NUM_THREADS) aux_s[e] = 0.0f;   // ordered by the block syncs of the first stage below
 
-    if (p.fused) {
-        // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output, moe.cuh:43-48).
-        // Done first: the stores drain under the router's load latencies, long before anybody can add into these rows
-        // (an expert only sees a token after this CTA's dispatch acknowledgement, which is ordered behind these stores).
-        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-        const int vec_per_row = H >> 3;
-        for (int i = tid; i < n_tok * vec_per_row; i += NUM_THREADS)
-            st_global_v4(p.out_acc + (size_t)t0 * H + (size_t)i * 8, z);
-    }
     uint64_t* wgbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_WG;   // initialised in the kernel prologue
     uint32_t wgphase = 0;
     const int EG = E < 128 ? E : 128;                      // experts staged per group
@@ -373,6 +364,17 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }
         __syncthreads();
         if (tid == 0) trace_stamp(p, 11);
+        if (p.fused && s0 == 0) {
+            // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output,
+            // moe.cuh:43-48).  Issued here, after the GEMV's loads: the stores drain under the softmax / top-k / slot-rank
+            // / grid-barrier stretch that follows, which issues no global loads of its own -- at the very start of the
+            // kernel they delayed the x / Wg loads by 3 us -- and long before anybody can add into these rows (an expert
+            // only sees a token after this CTA's dispatch acknowledgement, which is ordered behind these stores).
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+            const int vec_per_row = H >> 3;
+            for (int i = tid; i < n_tok * vec_per_row; i += NUM_THREADS)
+                st_global_v4(p.out_acc + (size_t)t0 * H + (size_t)i * 8, z);
+        }
         if (E <= 32) {
             // E <= 32: a group of LPT = pow2ceil(E) lanes per token.  Every lane of the group runs the reference's
             // sequential online-softmax recurrence itself (gate.cuh:575-584; E <= 32 steps on broadcast smem reads, so the
@@ -618,13 +620,21 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             }
         }
     }
-    // Row copies through the TMA engine: the chunk's token rows are contiguous in x, so one bulk load stages up to
-    // 128 KiB of them in shared memory and every kept (token, pick) pair is one bulk store of a whole row into the
-    // owner rank's receive buffer (peer-mapped over NVLink).  No per-lane load/store latency chains.
+    // Row copies.  The chunk's token rows are contiguous in x, so one bulk load stages up to 128 KiB of them in shared
+    // memory (the first group was requested at the end of the router).  From there
+    //   * rows for experts on THIS rank: one cp.async.bulk store per row through the TMA engine (no per-lane chains);
+    //     they land in ~4 us and are acknowledged first (gpu-scope release), so the expert FFN can start on the local
+    //     packets while
+    //   * rows for experts on OTHER ranks cross NVLink as plain 16-byte peer stores issued by all dispatch threads
+    //     (fire and forget -- the link, not the issue rate, bounds them: S*k*(1-1/W)*H*2 bytes at ~770 GB/s).  Only the
+    //     thread that acknowledges them waits (system-scope release) -- warp 2, which has no other duty yet -- while
+    //     warps 4-11 go on to their epilogue role.
     uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;   // initialised in the kernel prologue
     uint8_t* x_s = smem;   // the router's Wg / logits scratch is free now
     const int row_bytes = H * 2;
     const int rows_per_group = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
+    const int vec_per_row = H >> 3;
+    const bool any_remote = p.W > 1;
     uint32_t xphase = 0;
     for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
         const int rows = min(rows_per_group, n_tok - g0);
@@ -634,7 +644,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         }
         mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 900);
         xphase ^= 1;
-        for (int i = tid; i < rows * k; i += DISP_THREADS) {
+        for (int i = tid; i < rows * k; i += DISP_THREADS) {   // one thread per (token, pick): slot, routing record, local row
             const int tl = i / k, j = i - tl * k;
             const int ti = g0 + tl, t = t0 + ti;
             const int e = sel_e[ti * k + j];
@@ -651,38 +661,77 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
                     m.w = 0u;
                     st_global_v4(p.peer_recv_meta[owner] + row, m);
                 }
-                bulk_store_1d(p.peer_recv_x[owner] + row * H, x_s + (size_t)tl * row_bytes, (uint32_t)row_bytes);
+                if (owner == p.rank)
+                    bulk_store_1d(p.recv_x + row * H, x_s + (size_t)tl * row_bytes, (uint32_t)row_bytes);
             }
         }
         bulk_commit_group();
-        if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the stores have read it
+        if (any_remote) {   // remote rows: all threads stream 16-byte pieces smem -> peer memory
+            const int n_vec = rows * k * vec_per_row;
+            for (int i = tid; i < n_vec; i += DISP_THREADS) {
+                const int ent = i / vec_per_row, v = i - ent * vec_per_row;
+                const int tl = ent / k, ti = g0 + tl;
+                const int e = sel_e[ti * k + (ent - tl * k)];
+                const int owner = e / p.nLx;
+                if (owner == p.rank) continue;
+                const int s = base_s[e] + rank_s[ti * k + (ent - tl * k)];
+                if (s >= p.EC) continue;
+                const size_t row = (size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + s;
+                const uint4 val = *reinterpret_cast<const uint4*>(x_s + (size_t)tl * row_bytes + (size_t)v * 16);
+                st_global_v4(p.peer_recv_x[owner] + row * H + (size_t)v * 8, val);
+            }
+        }
+        if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the bulk stores have read it
             bulk_wait_group_read0();
             disp_sync();
         }
     }
-    bulk_wait_group0();        // this thread's row stores are complete ...
+    bulk_wait_group0();        // this thread's local row stores are complete ...
     fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
     disp_sync();
     if (tid == 0) trace_stamp(p, 9);
     // acknowledge: this chunk's rows of expert e occupy slots [base, base + own) of packet (me, e), cut at EC.  The
-    // release covers every dispatch thread's completed row / record stores (observed through the barrier above).
-    for (int e = tid; e < E; e += DISP_THREADS) {
-        const int lo = base_s[e];
-        const int hi = min(lo + own_s[e], p.EC);
-        if (hi > lo) {
+    // release covers every dispatch thread's row / record stores (observed through the barrier above).  Lanes of warp 2
+    // only (tid < 32): first the local experts (same GPU: the cheap fence); the slot ranges of the remote experts are
+    // taken into registers, the stage area is handed to the TMA producer, and only then does the system-scope release
+    // wait for the peer stores.
+    if (tid < 32) {
+        auto ack = [&](int e, int lo, int hi, bool local) {
+            if (hi <= lo) return;
             const int owner = e / p.nLx, le = e - owner * p.nLx;
             unsigned int* ctr = p.peer_recv_rows[owner] + ((size_t)par * p.num_pkts + (size_t)(p.rank * p.nLx + le)) * p.TCM;
             for (int b = lo / BLOCK_M; b <= (hi - 1) / BLOCK_M; ++b) {
                 const int n = min(hi, (b + 1) * BLOCK_M) - max(lo, b * BLOCK_M);
-                if (owner == p.rank) red_release_gpu_add_u32(ctr + b, (unsigned int)n);   // same GPU: the cheaper fence
+                if (local) red_release_gpu_add_u32(ctr + b, (unsigned int)n);
                 else red_release_sys_add_u32(ctr + b, (unsigned int)n);
             }
+        };
+        const int first_local = p.rank * p.nLx;
+        for (int e = first_local + tid; e < first_local + p.nLx; e += 32) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), true);
+        constexpr int RMAX = 8;   // remote experts per lane kept in registers (E <= 256); beyond that: acknowledge first
+        int rlo[RMAX], rhi[RMAX];
+        const bool in_regs = any_remote && E <= 32 * RMAX;
+        if (any_remote) {
+#pragma unroll
+            for (int i = 0; i < RMAX; ++i) {
+                const int e = tid + 32 * i;
+                const bool remote = e < E && (e < first_local || e >= first_local + p.nLx);
+                rlo[i] = remote ? base_s[e] : 0;
+                rhi[i] = remote ? min(base_s[e] + own_s[e], p.EC) : 0;
+            }
+            if (!in_regs)
+                for (int e = tid; e < E; e += 32)
+                    if (e < first_local || e >= first_local + p.nLx) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), false);
+        }
+        __syncwarp();
+        // from here this CTA's dispatch no longer touches the stage area (the remote copies have read it, too): release
+        // the TMA producer, which entered its role right after the grid barrier and may already hold a tile
+        if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
+        if (in_regs) {
+#pragma unroll
+            for (int i = 0; i < RMAX; ++i) ack(tid + 32 * i, rlo[i], rhi[i], false);
         }
     }
-    disp_sync();
-    // from here this CTA's dispatch no longer touches the stage area: release the TMA producer (which entered its role
-    // right after the grid barrier and may already hold a tile whose rows arrived early)
-    if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
 }
 
 // ============================================================================================================

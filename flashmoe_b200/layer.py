@@ -17,6 +17,7 @@ class MoEOutput(NamedTuple):
     topk_idx: torch.Tensor            # [S, k] int32   expert picked per token, in pick order
     topk_weight: torch.Tensor         # [S, k] bf16    gateOut[t, e_j] (bf16-rounded softmax probability)
     slot: torch.Tensor                # [S, k] int32   slot in the (rank, expert) packet; >= capacity means dropped
+    aux_loss: Optional[torch.Tensor] = None   # is_training = 1: f32 [2E+1] = gML[E] | gMeC[E] | load-balancing loss
 
 
 class FlashMoELayer(torch.nn.Module):
@@ -57,7 +58,8 @@ class FlashMoELayer(torch.nn.Module):
         idx = torch.from_numpy(self.ctx.read("topk_idx"))
         w = torch.from_numpy(self.ctx.read("topk_w").view("int16")).view(torch.bfloat16)
         slot = torch.from_numpy(self.ctx.read("slot"))
-        return MoEOutput(out, idx, w, slot)
+        aux = torch.from_numpy(self.ctx.read("aux_loss")) if self.cfg.is_training else None
+        return MoEOutput(out, idx, w, slot, aux)
 
     def extra_repr(self) -> str:
         c = self.cfg

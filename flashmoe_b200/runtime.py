@@ -277,6 +277,16 @@ class MoEContext:
 
         return torch.as_tensor(_Raw(), device=self.device).view(torch.bfloat16).view(shape)
 
+    def sync_ranks(self, group=None) -> None:
+        """Optional host-side rendezvous before a forward (world > 1).  The kernel's waits are bounded (default 120 s,
+        `timeout_ms`) and end in a trap when a peer never shows up; ranks whose skew may exceed that -- first-iteration
+        compilation, checkpoint I/O, a debugger -- can line up here first."""
+        if self.world > 1:
+            import torch.distributed as dist
+
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=group)
+
     def set_trace(self, enable: bool) -> None:
         _lib.check(self._L.fm_set_trace(self._ctx, 1 if enable else 0))
 
