@@ -620,20 +620,20 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             }
         }
     }
-    // Row copies.  The chunk's token rows are contiguous in x, so one bulk load stages up to 128 KiB of them in shared
-    // memory (the first group was requested at the end of the router).  From there
-    //   * rows for experts on THIS rank: one cp.async.bulk store per row through the TMA engine (no per-lane chains);
-    //     they land in ~4 us and are acknowledged first (gpu-scope release), so the expert FFN can start on the local
-    //     packets while
-    //   * rows for experts on OTHER ranks cross NVLink as plain 16-byte peer stores issued by all dispatch threads
-    //     (fire and forget -- the link, not the issue rate, bounds them: S*k*(1-1/W)*H*2 bytes at ~770 GB/s).  Only the
-    //     thread that acknowledges them waits (system-scope release) -- warp 2, which has no other duty yet -- while
-    //     warps 4-11 go on to their epilogue role.
+    // Row copies.
+    //   * Rows for experts on THIS rank: the chunk's token rows are contiguous in x, so one bulk load stages up to 128 KiB
+    //     of them in shared memory (the first group was requested at the end of the router) and every kept (token, pick)
+    //     pair is one cp.async.bulk store of a whole row through the TMA engine (no per-lane chains).  They land in ~4 us
+    //     and are acknowledged at once (gpu-scope release); the stage area is handed to the TMA producer, so the expert
+    //     FFN starts on the local packets while
+    //   * rows for experts on OTHER ranks cross NVLink as 16-byte peer stores read straight from x (L2 hits), one row per
+    //     warp at a time.  The link bounds them (S*k*(1-1/W)*H*2 bytes at ~770 GB/s) and back-pressures the issuing
+    //     warps, which is why they come last; warp 2 then waits for them with a system-scope release before it
+    //     acknowledges -- it has no other duty yet -- while warps 4-11 go on to their epilogue role.
     uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;   // initialised in the kernel prologue
     uint8_t* x_s = smem;   // the router's Wg / logits scratch is free now
     const int row_bytes = H * 2;
     const int rows_per_group = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
-    const int vec_per_row = H >> 3;
     const bool any_remote = p.W > 1;
     uint32_t xphase = 0;
     for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
@@ -666,21 +666,6 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             }
         }
         bulk_commit_group();
-        if (any_remote) {   // remote rows: all threads stream 16-byte pieces smem -> peer memory
-            const int n_vec = rows * k * vec_per_row;
-            for (int i = tid; i < n_vec; i += DISP_THREADS) {
-                const int ent = i / vec_per_row, v = i - ent * vec_per_row;
-                const int tl = ent / k, ti = g0 + tl;
-                const int e = sel_e[ti * k + (ent - tl * k)];
-                const int owner = e / p.nLx;
-                if (owner == p.rank) continue;
-                const int s = base_s[e] + rank_s[ti * k + (ent - tl * k)];
-                if (s >= p.EC) continue;
-                const size_t row = (size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + s;
-                const uint4 val = *reinterpret_cast<const uint4*>(x_s + (size_t)tl * row_bytes + (size_t)v * 16);
-                st_global_v4(p.peer_recv_x[owner] + row * H + (size_t)v * 8, val);
-            }
-        }
         if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the bulk stores have read it
             bulk_wait_group_read0();
             disp_sync();
@@ -690,46 +675,74 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
     disp_sync();
     if (tid == 0) trace_stamp(p, 9);
-    // acknowledge: this chunk's rows of expert e occupy slots [base, base + own) of packet (me, e), cut at EC.  The
-    // release covers every dispatch thread's row / record stores (observed through the barrier above).  Lanes of warp 2
-    // only (tid < 32): first the local experts (same GPU: the cheap fence); the slot ranges of the remote experts are
-    // taken into registers, the stage area is handed to the TMA producer, and only then does the system-scope release
-    // wait for the peer stores.
+    // Acknowledgements: this chunk's rows of expert e occupy slots [base, base + own) of packet (me, e), cut at EC.  A
+    // release covers every dispatch thread's row / record stores observed through the preceding barrier.  Lanes of warp 2
+    // (tid < 32) acknowledge the local experts now; the slot ranges of the remote experts are taken into registers,
+    // because the stage area -- where base / own live -- is handed to the TMA producer before the remote rows move.
+    constexpr int RMAX = 8;   // remote experts per lane kept in registers (E <= 256); beyond that the producer waits
+    int rlo[RMAX], rhi[RMAX];
+    const bool in_regs = any_remote && E <= 32 * RMAX;
+    const int first_local = p.rank * p.nLx;
+    auto ack = [&](int e, int lo, int hi, bool local) {
+        if (hi <= lo) return;
+        const int owner = e / p.nLx, le = e - owner * p.nLx;
+        unsigned int* ctr = p.peer_recv_rows[owner] + ((size_t)par * p.num_pkts + (size_t)(p.rank * p.nLx + le)) * p.TCM;
+        for (int b = lo / BLOCK_M; b <= (hi - 1) / BLOCK_M; ++b) {
+            const int n = min(hi, (b + 1) * BLOCK_M) - max(lo, b * BLOCK_M);
+            if (local) red_release_gpu_add_u32(ctr + b, (unsigned int)n);
+            else red_release_sys_add_u32(ctr + b, (unsigned int)n);
+        }
+    };
     if (tid < 32) {
-        auto ack = [&](int e, int lo, int hi, bool local) {
-            if (hi <= lo) return;
-            const int owner = e / p.nLx, le = e - owner * p.nLx;
-            unsigned int* ctr = p.peer_recv_rows[owner] + ((size_t)par * p.num_pkts + (size_t)(p.rank * p.nLx + le)) * p.TCM;
-            for (int b = lo / BLOCK_M; b <= (hi - 1) / BLOCK_M; ++b) {
-                const int n = min(hi, (b + 1) * BLOCK_M) - max(lo, b * BLOCK_M);
-                if (local) red_release_gpu_add_u32(ctr + b, (unsigned int)n);
-                else red_release_sys_add_u32(ctr + b, (unsigned int)n);
-            }
-        };
-        const int first_local = p.rank * p.nLx;
         for (int e = first_local + tid; e < first_local + p.nLx; e += 32) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), true);
-        constexpr int RMAX = 8;   // remote experts per lane kept in registers (E <= 256); beyond that: acknowledge first
-        int rlo[RMAX], rhi[RMAX];
-        const bool in_regs = any_remote && E <= 32 * RMAX;
-        if (any_remote) {
 #pragma unroll
-            for (int i = 0; i < RMAX; ++i) {
-                const int e = tid + 32 * i;
-                const bool remote = e < E && (e < first_local || e >= first_local + p.nLx);
-                rlo[i] = remote ? base_s[e] : 0;
-                rhi[i] = remote ? min(base_s[e] + own_s[e], p.EC) : 0;
-            }
-            if (!in_regs)
-                for (int e = tid; e < E; e += 32)
-                    if (e < first_local || e >= first_local + p.nLx) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), false);
+        for (int i = 0; i < RMAX; ++i) {
+            const int e = tid + 32 * i;
+            const bool remote = any_remote && e < E && (e < first_local || e >= first_local + p.nLx);
+            rlo[i] = remote ? base_s[e] : 0;
+            rhi[i] = remote ? min(base_s[e] + own_s[e], p.EC) : 0;
         }
         __syncwarp();
-        // from here this CTA's dispatch no longer touches the stage area (the remote copies have read it, too): release
-        // the TMA producer, which entered its role right after the grid barrier and may already hold a tile
-        if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
+        // from here this CTA's dispatch no longer touches the stage area: release the TMA producer, which entered its role
+        // right after the grid barrier and may already hold a tile (E > 256 on several ranks: only after the remote acks)
+        if (tid == 0 && (in_regs || !any_remote)) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
+    }
+    if (!any_remote) return;
+    // remote rows: warp `wid` of the 9 dispatch warps takes entries wid, wid + 9, ...; the slot and the expert come from
+    // the routing tables this CTA wrote above (global memory; the smem copies may be gone), the row from x
+    {
+        const int wid = warp == 2 ? 0 : warp - 3;
+        const int vec_per_row = H >> 3;
+        for (int ent = wid; ent < n_tok * k; ent += DISP_THREADS / 32) {
+            const size_t gi = (size_t)t0 * k + ent;
+            const int e = p.topk_idx[gi];
+            const int owner = e / p.nLx;
+            if (owner == p.rank) continue;
+            const int s = p.slot[gi];
+            if (s >= p.EC) continue;
+            const __nv_bfloat16* src = p.x + (size_t)(t0 + ent / k) * H;
+            __nv_bfloat16* dst = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + s) * H;
+            for (int v0 = lane; v0 < vec_per_row; v0 += 128) {   // four 16-byte pieces per lane in flight
+                uint4 val[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (v0 + u * 32 < vec_per_row) val[u] = ld_global_nc_v4(src + (size_t)(v0 + u * 32) * 8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (v0 + u * 32 < vec_per_row) st_global_v4(dst + (size_t)(v0 + u * 32) * 8, val[u]);
+            }
+        }
+    }
+    disp_sync();   // every dispatch warp's peer stores are issued
+    if (tid < 32) {
         if (in_regs) {
 #pragma unroll
             for (int i = 0; i < RMAX; ++i) ack(tid + 32 * i, rlo[i], rhi[i], false);
+        } else {
+            for (int e = tid; e < E; e += 32)
+                if (e < first_local || e >= first_local + p.nLx) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), false);
+            __syncwarp();
+            if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
         }
     }
 }
