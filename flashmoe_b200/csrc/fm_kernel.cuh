@@ -795,105 +795,118 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
     int q = 0, qphase = 0, cursor = 0, n = 0;
     bool seen_remote = false;   // trace only: first tile of a packet from another rank
     for (;;) {
-        int kind = -1;
-        if (lane == 0) {
-            if (n >= 1) {  // bounded look-ahead: wait until the producer is close to finishing tile n-1
-                const int pq = (q + NSCHED - 1) % NSCHED;
-                mbar_wait(&prod_take[pq], ((n - 1) / NSCHED) & 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, 200 + pq);
-            }
-            TileInfo ti;
-            ti.kind = -1; ti.ntile = 0; ti.le = 0; ti.b_row = 0;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) { ti.pkt[h] = 0; ti.mblk[h] = 0; ti.rows[h] = 0; ti.src[h] = 0; ti.cnt[h] = 0; ti.gather[h] = 0; }
-            for (;;) {
-                const int id = (int)atomicAdd(p.claim, 1u);
-                if (id >= p.total_items) break;
-                if (n < 16) trace_stamp(p, 112 + n);   // claim time of tile n (ready time is slot 16+n)
-                while (id >= p.blocks[cursor + 1].start) ++cursor;
-                const TileBlock blk = p.blocks[cursor];
-                const int local = id - blk.start;
-                // item -> (row block(s), column tile); row blocks fastest.  Within-packet pairing: halves = row blocks
-                // 2m, 2m+1 of one packet.  Cross-source pairing (pkt2 >= 0): halves = row block m of two packets.
-                const bool cross = PAIR && blk.pkt2 >= 0;
-                const int m_items = (PAIR && !cross) ? (p.TCM + 1) / 2 : p.TCM;
-                const int m = local % m_items, nt = local / m_items;
-                const int le = blk.pkt % p.nLx;
-                bool any = false;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h >= nh) break;
-                    const int pkt = (h == 1 && cross) ? blk.pkt2 : blk.pkt;
-                    const int mb = cross ? m : (PAIR ? 2 * m + h : m);
-                    const int src = pkt / p.nLx;
-                    ti.pkt[h] = pkt; ti.mblk[h] = mb; ti.src[h] = src; ti.rows[h] = 0; ti.cnt[h] = 0; ti.gather[h] = 0;
-                    if (mb >= p.TCM) continue;
-                    // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
-                    unsigned long long f = ((unsigned long long)p.epoch << 32) | (unsigned int)p.S;   // dense: all S rows, in x
-                    bool stale = false;
-                    if (!p.dense && !(h == 1 && !cross)) {   // (within-packet pairing: the second half shares the flag)
-                        SpinGuard g;
-                        for (;;) {
-                            f = ld_acquire_sys_u64(p.recv_flag + pkt);
-                            const int ahead = (int)((unsigned int)(f >> 32) - p.epoch);
-                            if (ahead == 0) break;
-                            // The source rank is already in a LATER forward: it only gets there after every real tile of
-                            // this packet has been returned to it, so whatever item of the static superset is left here
-                            // is an empty row block.
-                            if (ahead > 0) { stale = true; break; }
-                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, pkt, (unsigned int)(f >> 32), p.epoch);
-                        }
-                    } else if (h == 1 && !cross) {
-                        if (ti.cnt[0] == 0 && ti.rows[0] == 0 && !any) stale = true;   // first half found the packet empty / stale
-                        f = ((unsigned long long)p.epoch << 32) | (unsigned int)ti.cnt[0];
+        if (lane == 0 && n >= 1) {  // bounded look-ahead: wait until the producer is close to finishing tile n-1
+            const int pq = (q + NSCHED - 1) % NSCHED;
+            mbar_wait(&prod_take[pq], ((n - 1) / NSCHED) & 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, 200 + pq);
+        }
+        __syncwarp();
+        // The whole warp walks the claim loop in lock-step; lane h resolves the dependencies of half h of the item (the
+        // two halves' flag / counter round trips overlap), lane 0 assembles and publishes the descriptor.
+        int kind = -1, nt = 0, le = 0;
+        int h_pkt = 0, h_mb = 0, h_src = 0, h_rows = 0, h_cnt = 0, h_gather = 0;
+        for (;;) {
+            int id = 0;
+            if (lane == 0) id = (int)atomicAdd(p.claim, 1u);
+            id = __shfl_sync(0xffffffffu, id, 0);
+            if (id >= p.total_items) break;
+            if (lane == 0 && n < 16) trace_stamp(p, 112 + n);   // claim time of tile n (ready time is slot 16+n)
+            while (id >= p.blocks[cursor + 1].start) ++cursor;
+            const TileBlock blk = p.blocks[cursor];
+            const int local = id - blk.start;
+            // item -> (row block(s), column tile); row blocks fastest.  Within-packet pairing: halves = row blocks
+            // 2m, 2m+1 of one packet.  Cross-source pairing (pkt2 >= 0): halves = row block m of two packets.
+            const bool cross = PAIR && blk.pkt2 >= 0;
+            const int m_items = (PAIR && !cross) ? (p.TCM + 1) / 2 : p.TCM;
+            const int m = local % m_items;
+            nt = local / m_items;
+            le = blk.pkt % p.nLx;
+            const int h = lane;
+            h_pkt = (h == 1 && cross) ? blk.pkt2 : blk.pkt;
+            h_mb = cross ? m : (PAIR ? 2 * m + (h & 1) : m);
+            h_src = h_pkt / p.nLx;
+            h_rows = 0; h_cnt = 0; h_gather = 0;
+            if (h < nh && h_mb < p.TCM) {
+                const bool same_gpu = h_src == p.rank;   // flag and counters written from this GPU: gpu scope suffices
+                // wait for the packet (src, le): flag = {epoch, rows}  (reference subscriber.cuh:52-185)
+                unsigned long long f = ((unsigned long long)p.epoch << 32) | (unsigned int)p.S;   // dense: all S rows, in x
+                bool stale = false;
+                if (!p.dense) {
+                    SpinGuard g;
+                    for (;;) {
+                        f = same_gpu ? ld_acquire_gpu_u64(p.recv_flag + h_pkt) : ld_acquire_sys_u64(p.recv_flag + h_pkt);
+                        const int ahead = (int)((unsigned int)(f >> 32) - p.epoch);
+                        if (ahead == 0) break;
+                        // The source rank is already in a LATER forward: it only gets there after every real tile of
+                        // this packet has been returned to it, so whatever item of the static superset is left here
+                        // is an empty row block.
+                        if (ahead > 0) { stale = true; break; }
+                        g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_FLAG, h_pkt, (unsigned int)(f >> 32), p.epoch);
                     }
-                    if (stale) continue;
-                    const int cnt = (int)(f & 0xffffffffull);
-                    ti.cnt[h] = cnt;
+                }
+                if (!stale) {
+                    h_cnt = (int)(f & 0xffffffffull);
                     if (h == 0 || cross) {   // once per packet and GEMM (its first item): bookkeeping that needs the count
-                        if (local == 0 && blk.kind == 0 && !p.dense) p.recv_cnt[pkt] = cnt;
-                        if (p.fused && local == 0 && blk.kind == 1 && cnt == 0)   // nothing to contribute: tell the source now
-                            st_release_sys_u64(p.peer_done_flag[src] + (size_t)(p.rank * p.nLx + le),
+                        if (local == 0 && blk.kind == 0 && !p.dense) p.recv_cnt[h_pkt] = h_cnt;
+                        if (p.fused && local == 0 && blk.kind == 1 && h_cnt == 0)   // nothing to contribute: tell the source now
+                            st_release_sys_u64(p.peer_done_flag[h_src] + (size_t)(p.rank * p.nLx + le),
                                                (unsigned long long)p.epoch << 32);
                     }
-                    const int rows = max(0, min(BLOCK_M, cnt - mb * BLOCK_M));
-                    ti.rows[h] = rows;
-                    if (rows == 0) continue;   // empty row block of the static superset
-                    any = true;
+                    h_rows = max(0, min(BLOCK_M, h_cnt - h_mb * BLOCK_M));
+                }
+                if (h_rows > 0) {
                     SpinGuard g;
+                    const unsigned int* rctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + h_pkt) * p.TCM + h_mb;
                     if (blk.kind == 1) {  // GEMM1 needs the whole h row block (reference notifyNext, processor.cuh:490-615)
-                        const unsigned int* ctr = p.g0_done + (size_t)pkt * p.TCM + mb;
+                        const unsigned int* ctr = p.g0_done + (size_t)h_pkt * p.TCM + h_mb;
                         while (ld_acquire_gpu_u32(ctr) < (unsigned int)p.TN0)
-                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, pkt, mb, 0);
-                        if (p.gather && p.fused && src == p.rank && (p.phase_mask & 1u)) {
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_G0_DONE, h_pkt, h_mb, 0);
+                        if (p.gather && p.fused && same_gpu && (p.phase_mask & 1u)) {
                             // the block's GEMM0 tiles may all have run in gather mode, i.e. before its row copies and
                             // routing records landed: the combine epilogue reads those records, so order behind their ack
-                            const unsigned int* rctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + pkt) * p.TCM + mb;
-                            while (ld_acquire_sys_u32(rctr) < (unsigned int)rows)
-                                g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, pkt, mb, rows);
+                            while (ld_acquire_gpu_u32(rctr) < (unsigned int)h_rows)
+                                g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, h_pkt, h_mb, h_rows);
                         }
                     } else if ((p.phase_mask & 1u) && !p.dense) {  // GEMM0 needs the rows of this block to have landed (dispatch acks)
-                        const unsigned int* ctr = p.recv_rows + ((size_t)(p.epoch & 1u) * p.num_pkts + pkt) * p.TCM + mb;
                         // local packet: the token table of the block is acknowledged before its row copies -- if it is
-                        // complete while the rows are not, the producer gathers the rows from x itself
-                        const unsigned int* tctr = (p.gather && src == p.rank)
-                            ? p.tok_rows + ((size_t)(p.epoch & 1u) * p.nLx + le) * p.TCM + mb : nullptr;
+                        // complete while the rows are not, the producer gathers the rows from x itself (FM_GATHER=1)
+                        const unsigned int* tctr = (p.gather && same_gpu)
+                            ? p.tok_rows + ((size_t)(p.epoch & 1u) * p.nLx + le) * p.TCM + h_mb : nullptr;
                         for (;;) {
-                            if (ld_acquire_sys_u32(ctr) >= (unsigned int)rows) break;
-                            if (tctr != nullptr && ld_acquire_gpu_u32(tctr) >= (unsigned int)rows) { ti.gather[h] = 1; break; }
-                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, pkt, mb, rows);
+                            const unsigned int got = same_gpu ? ld_acquire_gpu_u32(rctr) : ld_acquire_sys_u32(rctr);
+                            if (got >= (unsigned int)h_rows) break;
+                            if (tctr != nullptr && ld_acquire_gpu_u32(tctr) >= (unsigned int)h_rows) { h_gather = 1; break; }
+                            g.tick(p.dbg, p.timeout_ns, FM_TRAP_RECV_ROWS, h_pkt, h_mb, h_rows);
                         }
                     }
                 }
-                if (!any) continue;
-                ti.kind = blk.kind; ti.ntile = nt; ti.le = le;
-                const int bn_item = p.bn[blk.kind];
-                // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
-                // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
-                ti.b_row = (blk.kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * bn_item;
-                break;
             }
+            __syncwarp();
+            const bool any = __any_sync(0xffffffffu, h_rows > 0 && lane < nh);
+            if (!any) continue;   // every half is an empty row block of the static superset
+            kind = blk.kind;
+            break;
+        }
+        // lane 0 collects both halves
+        TileInfo ti;
+        ti.kind = kind; ti.ntile = nt; ti.le = le;
+        // expert_weights [nLx,2,P,H]: W_up(le) starts at row le*2*P of the [.,H] view; W_down(le) (the [P,H]
+        // block flat-viewed as [H,P]) starts at row (le*2+1)*H of the [.,P] view.
+        ti.b_row = kind < 0 ? 0 : (kind == 0 ? le * 2 * p.P : (le * 2 + 1) * p.H) + nt * p.bn[kind];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            ti.pkt[h] = __shfl_sync(0xffffffffu, h_pkt, h);
+            ti.mblk[h] = __shfl_sync(0xffffffffu, h_mb, h);
+            ti.src[h] = __shfl_sync(0xffffffffu, h_src, h);
+            ti.rows[h] = (kind >= 0 && h < nh) ? __shfl_sync(0xffffffffu, h_rows, h) : 0;
+            ti.cnt[h] = __shfl_sync(0xffffffffu, h_cnt, h);
+            ti.gather[h] = (kind >= 0 && h < nh) ? __shfl_sync(0xffffffffu, h_gather, h) : 0;
+        }
+        if (lane == 0) {
             if (ti.kind >= 0 && n < 16) trace_stamp(p, 16 + n);
-            if (ti.kind >= 0 && (ti.src[0] != p.rank || (PAIR && ti.src[1] != p.rank)) && !seen_remote) { seen_remote = true; trace_stamp(p, 13); }
+            if (ti.kind >= 0 && (ti.src[0] != p.rank || (PAIR && ti.rows[1] > 0 && ti.src[1] != p.rank)) && !seen_remote) {
+                seen_remote = true;
+                trace_stamp(p, 13);
+            }
             mbar_wait(&sched_empty[q], qphase ^ 1, p.dbg, p.timeout_ns, FM_TRAP_MBAR_SCHED_EMPTY, q);
             ring[q] = ti;
             if (PAIR) {  // mirror the descriptor into the peer CTA's ring over DSMEM, then signal both rings
@@ -904,9 +917,7 @@ __device__ __forceinline__ void ffn_scheduler(const FmParams& p, uint8_t* smem, 
                 mbar_arrive_cluster(&sched_full[q], 1);
             }
             mbar_arrive(&sched_full[q]);
-            kind = ti.kind;
         }
-        kind = __shfl_sync(0xffffffffu, kind, 0);
         if (++q == NSCHED) { q = 0; qphase ^= 1; }
         ++n;
         if (kind < 0) break;
