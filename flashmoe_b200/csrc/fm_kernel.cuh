@@ -250,6 +250,26 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     if (p.aux != nullptr)
         for (int e = tid; e < E; e += NUM_THREADS) aux_s[e] = 0.0f;   // ordered by the block syncs of the first stage below
 
+    if (p.fused && warp == EPI_WARP0) {
+        // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output,
+        // moe.cuh:43-48).  Done by the TMA engine from a zeroed piece of the (still unused) epilogue staging area, so no
+        // thread stalls on a store queue: as plain stores this cost 1.5-3 us on the router's critical path wherever it was
+        // placed.  Warp 4 issues the bulk stores here and waits for them in dispatch_phase before it acknowledges the local
+        // rows -- an expert only adds into a token's row after that acknowledgement (or a later one of this CTA).
+        uint8_t* zbuf = smem + OFF_EPI;
+        const int row_bytes = H * 2, zbytes = min(row_bytes, 8192);
+        for (int i = lane * 16; i < zbytes; i += 512) *reinterpret_cast<uint4*>(zbuf + i) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int pieces = row_bytes / zbytes;   // H is a multiple of 64, rows above 8 KiB are multiples of 8 KiB or handled below
+        for (int i = lane; i < n_tok * pieces; i += 32)
+            bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)t0 * H) + (size_t)i * zbytes, zbuf, (uint32_t)zbytes);
+        const int rem = row_bytes - pieces * zbytes;   // (row_bytes not a multiple of 8 KiB: the tail of every row)
+        if (rem > 0)
+            for (int i = lane; i < n_tok; i += 32)
+                bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)(t0 + i) * H) + (size_t)pieces * zbytes, zbuf, (uint32_t)rem);
+        bulk_commit_group();
+    }
     uint64_t* wgbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_WG;   // initialised in the kernel prologue
     uint32_t wgphase = 0;
     const int EG = E < 128 ? E : 128;                      // experts staged per group
@@ -364,17 +384,6 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }
         __syncthreads();
         if (tid == 0) trace_stamp(p, 11);
-        if (p.fused && s0 == 0) {
-            // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output,
-            // moe.cuh:43-48).  Issued here, after the GEMV's loads: the stores drain under the softmax / top-k / slot-rank
-            // / grid-barrier stretch that follows, which issues no global loads of its own -- at the very start of the
-            // kernel they delayed the x / Wg loads by 3 us -- and long before anybody can add into these rows (an expert
-            // only sees a token after this CTA's dispatch acknowledgement, which is ordered behind these stores).
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            const int vec_per_row = H >> 3;
-            for (int i = tid; i < n_tok * vec_per_row; i += NUM_THREADS)
-                st_global_v4(p.out_acc + (size_t)t0 * H + (size_t)i * 8, z);
-        }
         if (E <= 32) {
             // E <= 32: a group of LPT = pow2ceil(E) lanes per token.  Every lane of the group runs the reference's
             // sequential online-softmax recurrence itself (gate.cuh:575-584; E <= 32 steps on broadcast smem reads, so the
@@ -621,69 +630,24 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         }
     }
     // Row copies.
-    //   * Rows for experts on THIS rank: the chunk's token rows are contiguous in x, so one bulk load stages up to 128 KiB
-    //     of them in shared memory (the first group was requested at the end of the router) and every kept (token, pick)
-    //     pair is one cp.async.bulk store of a whole row through the TMA engine (no per-lane chains).  They land in ~4 us
-    //     and are acknowledged at once (gpu-scope release); the stage area is handed to the TMA producer, so the expert
-    //     FFN starts on the local packets while
-    //   * rows for experts on OTHER ranks cross NVLink as 16-byte peer stores read straight from x (L2 hits), one row per
-    //     warp at a time.  The link bounds them (S*k*(1-1/W)*H*2 bytes at ~770 GB/s) and back-pressures the issuing
-    //     warps, which is why they come last; warp 2 then waits for them with a system-scope release before it
-    //     acknowledges -- it has no other duty yet -- while warps 4-11 go on to their epilogue role.
+    //   * Rows for experts on THIS rank (warps 4-11): the chunk's token rows are contiguous in x, so one bulk load stages up
+    //     to 128 KiB of them in shared memory (the first group was requested at the end of the router) and every kept
+    //     (token, pick) pair is one cp.async.bulk store of a whole row through the TMA engine (no per-lane chains).  They
+    //     land in ~4 us and are acknowledged at once (gpu-scope release); the stage area is handed to the TMA producer, the
+    //     warps become epilogue warps, and the expert FFN starts on the local packets while
+    //   * rows for experts on OTHER ranks (warp 2, from the moment the slots are known) cross NVLink as 16-byte peer stores
+    //     read straight from x (L2 hits), sixteen pieces per lane in flight.  The link bounds them (S*k*(1-1/W)*H*2 bytes
+    //     at ~770 GB/s) and back-pressures the issuing warp -- which has no other duty until the first tile needs
+    //     publishing; it then waits for the stores with a system-scope release and acknowledges them.
     uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;   // initialised in the kernel prologue
     uint8_t* x_s = smem;   // the router's Wg / logits scratch is free now
     const int row_bytes = H * 2;
     const int rows_per_group = max(1, min(n_tok, G_XROWS_BYTES / row_bytes));
     const bool any_remote = p.W > 1;
-    uint32_t xphase = 0;
-    for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
-        const int rows = min(rows_per_group, n_tok - g0);
-        if (tid == 0 && g0 > 0) {   // group 0 was requested at the end of the router (gate_phase)
-            mbar_arrive_expect_tx(xbar, (uint32_t)(rows * row_bytes));
-            bulk_load_1d(x_s, p.x + (size_t)(t0 + g0) * H, (uint32_t)(rows * row_bytes), xbar);
-        }
-        mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 900);
-        xphase ^= 1;
-        for (int i = tid; i < rows * k; i += DISP_THREADS) {   // one thread per (token, pick): slot, routing record, local row
-            const int tl = i / k, j = i - tl * k;
-            const int ti = g0 + tl, t = t0 + ti;
-            const int e = sel_e[ti * k + j];
-            const int s = base_s[e] + rank_s[ti * k + j];
-            p.slot[(size_t)t * k + j] = s;
-            if (s < p.EC) {
-                const int owner = e / p.nLx, le = e - owner * p.nLx;
-                const size_t row = (size_t)(p.rank * p.nLx + le) * p.pEC + s;
-                if (p.fused) {   // what the expert's GEMM1 epilogue needs to combine this row
-                    uint4 m;
-                    m.x = (unsigned int)t;
-                    m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
-                    m.z = __float_as_uint(p.mcw[t]);
-                    m.w = 0u;
-                    st_global_v4(p.peer_recv_meta[owner] + row, m);
-                }
-                if (owner == p.rank)
-                    bulk_store_1d(p.recv_x + row * H, x_s + (size_t)tl * row_bytes, (uint32_t)row_bytes);
-            }
-        }
-        bulk_commit_group();
-        if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the bulk stores have read it
-            bulk_wait_group_read0();
-            disp_sync();
-        }
-    }
-    bulk_wait_group0();        // this thread's local row stores are complete ...
-    fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
-    disp_sync();
-    if (tid == 0) trace_stamp(p, 9);
-    // Acknowledgements: this chunk's rows of expert e occupy slots [base, base + own) of packet (me, e), cut at EC.  A
-    // release covers every dispatch thread's row / record stores observed through the preceding barrier.  Lanes of warp 2
-    // (tid < 32) acknowledge the local experts now; the slot ranges of the remote experts are taken into registers,
-    // because the stage area -- where base / own live -- is handed to the TMA producer before the remote rows move.
-    constexpr int RMAX = 8;   // remote experts per lane kept in registers (E <= 256); beyond that the producer waits
-    int rlo[RMAX], rhi[RMAX];
-    const bool in_regs = any_remote && E <= 32 * RMAX;
     const int first_local = p.rank * p.nLx;
     auto ack = [&](int e, int lo, int hi, bool local) {
+        // this chunk's rows of expert e occupy slots [lo, hi) of packet (me, e): add the rows landed per 128-row block.
+        // The release covers every store of the threads that met at the preceding barrier.
         if (hi <= lo) return;
         const int owner = e / p.nLx, le = e - owner * p.nLx;
         unsigned int* ctr = p.peer_recv_rows[owner] + ((size_t)par * p.num_pkts + (size_t)(p.rank * p.nLx + le)) * p.TCM;
@@ -693,57 +657,145 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             else red_release_sys_add_u32(ctr + b, (unsigned int)n);
         }
     };
-    if (tid < 32) {
-        for (int e = first_local + tid; e < first_local + p.nLx; e += 32) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), true);
-#pragma unroll
-        for (int i = 0; i < RMAX; ++i) {
-            const int e = tid + 32 * i;
-            const bool remote = any_remote && e < E && (e < first_local || e >= first_local + p.nLx);
-            rlo[i] = remote ? base_s[e] : 0;
-            rhi[i] = remote ? min(base_s[e] + own_s[e], p.EC) : 0;
+    constexpr int LOCAL_THREADS = DISP_THREADS - 32;   // warps 4..11
+    if (warp != 2) {
+        // ---------------------------------------------------------------- warps 4-11: slots, routing records, local rows
+        const int ltid = tid - 32;
+        uint32_t xphase = 0;
+        for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
+            const int rows = min(rows_per_group, n_tok - g0);
+            if (ltid == 0 && g0 > 0) {   // group 0 was requested at the end of the router (gate_phase)
+                mbar_arrive_expect_tx(xbar, (uint32_t)(rows * row_bytes));
+                bulk_load_1d(x_s, p.x + (size_t)(t0 + g0) * H, (uint32_t)(rows * row_bytes), xbar);
+            }
+            mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 900);
+            xphase ^= 1;
+            for (int i = ltid; i < rows * k; i += LOCAL_THREADS) {   // one thread per (token, pick)
+                const int tl = i / k, j = i - tl * k;
+                const int ti = g0 + tl, t = t0 + ti;
+                const int e = sel_e[ti * k + j];
+                const int s = base_s[e] + rank_s[ti * k + j];
+                p.slot[(size_t)t * k + j] = s;
+                if (s < p.EC) {
+                    const int owner = e / p.nLx, le = e - owner * p.nLx;
+                    const size_t row = (size_t)(p.rank * p.nLx + le) * p.pEC + s;
+                    if (p.fused) {   // what the expert's GEMM1 epilogue needs to combine this row
+                        uint4 m;
+                        m.x = (unsigned int)t;
+                        m.y = __float_as_uint(__bfloat162float(p.topk_w[(size_t)t * k + j]));
+                        m.z = __float_as_uint(p.mcw[t]);
+                        m.w = 0u;
+                        st_global_v4(p.peer_recv_meta[owner] + row, m);
+                    }
+                    if (owner == p.rank)
+                        bulk_store_1d(p.recv_x + row * H, x_s + (size_t)tl * row_bytes, (uint32_t)row_bytes);
+                }
+            }
+            bulk_commit_group();
+            if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the bulk stores have read it
+                bulk_wait_group_read0();
+                asm volatile("bar.sync 4, 256;" ::: "memory");
+            }
         }
-        __syncwarp();
-        // from here this CTA's dispatch no longer touches the stage area: release the TMA producer, which entered its role
-        // right after the grid barrier and may already hold a tile (E > 256 on several ranks: only after the remote acks)
-        if (tid == 0 && (in_regs || !any_remote)) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
+        if (any_remote) asm volatile("bar.arrive 3, 288;" ::: "memory");   // every slot (p.slot) is written: warp 2 may start
+        bulk_wait_group0();        // this thread's local row stores (and warp 4's zero-fill stores) are complete ...
+        fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
+        asm volatile("bar.sync 4, 256;" ::: "memory");
+        if (any_remote) asm volatile("bar.arrive 6, 288;" ::: "memory");   // local rows + zero-fill complete (warp 2's acks wait for this)
+        if (ltid == 0) trace_stamp(p, 9);
+        if (any_remote) asm volatile("bar.sync 5, 288;" ::: "memory");   // warp 2 has taken what it needs from the stage area
+        if (ltid < 32) {   // warp 4: acknowledge the local experts, then hand the stage area to the TMA producer
+            for (int e = first_local + ltid; e < first_local + p.nLx; e += 32) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), true);
+            __syncwarp();
+            // (more than 256 experts on several ranks: warp 2 still needs base / own for its acknowledgements and releases)
+            if (ltid == 0 && (!any_remote || E <= 256)) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
+        }
+        return;
     }
+    // -------------------------------------------------------------------- warp 2
     if (!any_remote) return;
-    // remote rows: warp `wid` of the 9 dispatch warps takes entries wid, wid + 9, ...; the slot and the expert come from
-    // the routing tables this CTA wrote above (global memory; the smem copies may be gone), the row from x
+    // the slot ranges of the remote experts go into registers (E <= 256) before the stage area -- where base / own live --
+    // is released by warp 4; beyond that the release waits for this warp
+    constexpr int RMAX = 8;
+    int rlo[RMAX], rhi[RMAX];
+    const bool in_regs = E <= 32 * RMAX;
+#pragma unroll
+    for (int i = 0; i < RMAX; ++i) {
+        const int e = lane + 32 * i;
+        const bool remote = in_regs && e < E && (e < first_local || e >= first_local + p.nLx);
+        rlo[i] = remote ? base_s[e] : 0;
+        rhi[i] = remote ? min(base_s[e] + own_s[e], p.EC) : 0;
+    }
+    __syncwarp();
+    if (in_regs) asm volatile("bar.arrive 5, 288;" ::: "memory");   // done with the stage area
+    asm volatile("bar.sync 3, 288;" ::: "memory");                  // every slot of this chunk (p.slot) is written
     {
-        const int wid = warp == 2 ? 0 : warp - 3;
+        // Remote rows.  Entries are examined 32 at a time (lane j: entry base + j; expert and slot from the routing tables
+        // in global memory), then copied a few rows per step so that every lane has sixteen 16-byte loads in flight.
         const int vec_per_row = H >> 3;
-        for (int ent = wid; ent < n_tok * k; ent += DISP_THREADS / 32) {
-            const size_t gi = (size_t)t0 * k + ent;
-            const int e = p.topk_idx[gi];
-            const int owner = e / p.nLx;
-            if (owner == p.rank) continue;
-            const int s = p.slot[gi];
-            if (s >= p.EC) continue;
-            const __nv_bfloat16* src = p.x + (size_t)(t0 + ent / k) * H;
-            __nv_bfloat16* dst = p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + s) * H;
-            for (int v0 = lane; v0 < vec_per_row; v0 += 128) {   // four 16-byte pieces per lane in flight
-                uint4 val[4];
+        const int ppl = (vec_per_row + 31) >> 5;                         // pieces per lane per row
+        const int U = ppl >= 16 ? 16 : (ppl > 4 ? 8 : 4);                 // pieces per lane per row and step
+        const int R = 16 / U;                                             // rows per step
+        const int n_ent = n_tok * k;
+        for (int base = 0; base < n_ent; base += 32) {
+            const int ent = base + lane;
+            bool valid = false;
+            unsigned long long my_src = 0ull, my_dst = 0ull;
+            if (ent < n_ent) {
+                const size_t gi = (size_t)t0 * k + ent;
+                const int e = p.topk_idx[gi];
+                const int owner = e / p.nLx;
+                const int sl = p.slot[gi];
+                valid = owner != p.rank && sl < p.EC;
+                if (valid) {
+                    my_src = reinterpret_cast<unsigned long long>(p.x + (size_t)(t0 + ent / k) * H);
+                    my_dst = reinterpret_cast<unsigned long long>(
+                        p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + sl) * H);
+                }
+            }
+            unsigned int mask = __ballot_sync(0xffffffffu, valid);
+            while (mask != 0u) {
+                unsigned long long rs[4], rd[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (v0 + u * 32 < vec_per_row) val[u] = ld_global_nc_v4(src + (size_t)(v0 + u * 32) * 8);
+                for (int r = 0; r < 4; ++r) {
+                    const bool take = r < R && mask != 0u;
+                    const int l = take ? __ffs(mask) - 1 : 0;
+                    if (take) mask &= mask - 1u;
+                    rs[r] = __shfl_sync(0xffffffffu, my_src, l);
+                    rd[r] = __shfl_sync(0xffffffffu, my_dst, l);
+                    if (!take) { rs[r] = 0ull; rd[r] = 0ull; }
+                }
+                for (int c0 = 0; c0 < ppl; c0 += U) {   // (rows wider than 16 pieces per lane: several rounds)
+                    uint4 val[16];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (v0 + u * 32 < vec_per_row) st_global_v4(dst + (size_t)(v0 + u * 32) * 8, val[u]);
+                    for (int q = 0; q < 16; ++q) {
+                        const int r = q / U, v = (c0 + q % U) * 32 + lane;
+                        const unsigned long long sp = r == 0 ? rs[0] : (r == 1 ? rs[1] : (r == 2 ? rs[2] : rs[3]));
+                        if (sp != 0ull && v < vec_per_row) val[q] = ld_global_nc_v4(reinterpret_cast<const uint4*>(sp) + v);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int r = q / U, v = (c0 + q % U) * 32 + lane;
+                        const unsigned long long dp = r == 0 ? rd[0] : (r == 1 ? rd[1] : (r == 2 ? rd[2] : rd[3]));
+                        if (dp != 0ull && v < vec_per_row) st_global_v4(reinterpret_cast<uint4*>(dp) + v, val[q]);
+                    }
+                }
             }
         }
     }
-    disp_sync();   // every dispatch warp's peer stores are issued
-    if (tid < 32) {
-        if (in_regs) {
+    __syncwarp();
+    // the remote acknowledgements also tell the peers that this chunk's output rows are zeroed (TMA stores issued by warp 4
+    // in the router, completed before it arrives here) and that the routing records are written
+    asm volatile("bar.sync 6, 288;" ::: "memory");
+    if (in_regs) {
 #pragma unroll
-            for (int i = 0; i < RMAX; ++i) ack(tid + 32 * i, rlo[i], rhi[i], false);
-        } else {
-            for (int e = tid; e < E; e += 32)
-                if (e < first_local || e >= first_local + p.nLx) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), false);
-            __syncwarp();
-            if (tid == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
-        }
+        for (int i = 0; i < RMAX; ++i) ack(lane + 32 * i, rlo[i], rhi[i], false);
+    } else {
+        for (int e = lane; e < E; e += 32)
+            if (e < first_local || e >= first_local + p.nLx) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), false);
+        __syncwarp();
+        asm volatile("bar.arrive 5, 288;" ::: "memory");
+        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
     }
 }
 
@@ -1329,12 +1381,17 @@ __device__ __forceinline__ void ffn_publisher(const FmParams& p, uint8_t* smem, 
                         fence_proxy_async_global();
                         red_release_gpu_add_u32(p.g0_done + (size_t)my_pkt * p.TCM + my_mblk, 1u);
                     } else if (p.fused) {
+                        if (my_src == p.rank && p.out_acc == p.out) {
+                            // local packet, output left in place: nobody waits for a flag (see finish_fused) -- no fence,
+                            // no counter, no flag; kernel completion covers these adds
+                        } else {
                         fence_acq_rel_sys();   // this tile's adds are performed before the packet counter moves
                         const unsigned int old = atom_acq_rel_gpu_add_u32(p.pkt_done + my_pkt, 1u);
                         const unsigned int want = (unsigned int)(((ti.cnt[hh] + BLOCK_M - 1) / BLOCK_M) * p.TN1);
                         if (old + 1u == want) {   // every GEMM1 tile of packet (src, le) has been added into src's output
                             st_release_sys_u64(p.peer_done_flag[my_src] + (size_t)(p.rank * p.nLx + ti.le),
                                                (unsigned long long)p.epoch << 32);
+                        }
                         }
                     } else {
                         fence_acq_rel_sys();
@@ -1515,7 +1572,13 @@ __device__ __forceinline__ void combine_rows(const FmParams& p, int t0, int n_to
 // reported all of its contributions, then (W > 1) move my rows from the symmetric accumulator to the caller's tensor
 __device__ __forceinline__ void finish_fused(const FmParams& p, int t0, int n_tok) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // Contributions of experts on THIS GPU need no flag when the rows are left where they were accumulated (out == the
+    // accumulation target): they are complete when the kernel is, and nobody reads them before.  Only the experts on other
+    // ranks -- whose adds arrive over NVLink at their own pace -- must have reported; with a separate caller tensor (the
+    // copy below) the local ones must have, too.
+    const bool need_local = p.out_acc != p.out;
     for (int e = tid; e < p.E; e += NUM_THREADS) {
+        if (!need_local && e / p.nLx == p.rank) continue;
         SpinGuard g;
         while ((ld_acquire_sys_u64(p.done_flag + e) >> 32) != p.epoch)
             g.tick(p.dbg, p.timeout_ns, FM_TRAP_RET_FLAG, e, 0xD0E, 0);
