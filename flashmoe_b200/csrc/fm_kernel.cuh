@@ -250,26 +250,6 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     if (p.aux != nullptr)
         for (int e = tid; e < E; e += NUM_THREADS) aux_s[e] = 0.0f;   // ordered by the block syncs of the first stage below
 
-    if (p.fused && warp == EPI_WARP0) {
-        // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output,
-        // moe.cuh:43-48).  Done by the TMA engine from a zeroed piece of the (still unused) epilogue staging area, so no
-        // thread stalls on a store queue: as plain stores this cost 1.5-3 us on the router's critical path wherever it was
-        // placed.  Warp 4 issues the bulk stores here and waits for them in dispatch_phase before it acknowledges the local
-        // rows -- an expert only adds into a token's row after that acknowledgement (or a later one of this CTA).
-        uint8_t* zbuf = smem + OFF_EPI;
-        const int row_bytes = H * 2, zbytes = min(row_bytes, 8192);
-        for (int i = lane * 16; i < zbytes; i += 512) *reinterpret_cast<uint4*>(zbuf + i) = make_uint4(0u, 0u, 0u, 0u);
-        fence_proxy_async_smem();
-        __syncwarp();
-        const int pieces = row_bytes / zbytes;   // H is a multiple of 64, rows above 8 KiB are multiples of 8 KiB or handled below
-        for (int i = lane; i < n_tok * pieces; i += 32)
-            bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)t0 * H) + (size_t)i * zbytes, zbuf, (uint32_t)zbytes);
-        const int rem = row_bytes - pieces * zbytes;   // (row_bytes not a multiple of 8 KiB: the tail of every row)
-        if (rem > 0)
-            for (int i = lane; i < n_tok; i += 32)
-                bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)(t0 + i) * H) + (size_t)pieces * zbytes, zbuf, (uint32_t)rem);
-        bulk_commit_group();
-    }
     uint64_t* wgbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_WG;   // initialised in the kernel prologue
     uint32_t wgphase = 0;
     const int EG = E < 128 ? E : 128;                      // experts staged per group
@@ -384,6 +364,29 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }
         __syncthreads();
         if (tid == 0) trace_stamp(p, 11);
+        if (p.fused && s0 == 0 && warp == EPI_WARP0) {
+        // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output,
+        // moe.cuh:43-48).  Done by the TMA engine from a zeroed piece of the (still unused) epilogue staging area, so no
+        // thread stalls on a store queue (as plain stores this cost 1.5-3 us on the router's critical path wherever it was
+        // placed), and issued only now, after the GEMV: the engine works in order, and at the start of the kernel these
+        // stores sat in front of the gate-weight load (+5 us).  Warp 4 issues them here and waits for them in
+        // dispatch_phase before the local rows are acknowledged -- an expert only adds into a token's row after an
+        // acknowledgement of this CTA.
+        uint8_t* zbuf = smem + OFF_EPI;
+        const int row_bytes = H * 2, zbytes = min(row_bytes, 8192);
+        for (int i = lane * 16; i < zbytes; i += 512) *reinterpret_cast<uint4*>(zbuf + i) = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+        __syncwarp();
+        const int pieces = row_bytes / zbytes;   // H is a multiple of 64, rows above 8 KiB are multiples of 8 KiB or handled below
+        for (int i = lane; i < n_tok * pieces; i += 32)
+            bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)(t0 + i / pieces) * H) + (size_t)(i % pieces) * zbytes, zbuf,
+                          (uint32_t)zbytes);
+        const int rem = row_bytes - pieces * zbytes;   // (row_bytes not a multiple of 8 KiB: the tail of every row)
+        if (rem > 0)
+            for (int i = lane; i < n_tok; i += 32)
+                bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)(t0 + i) * H) + (size_t)pieces * zbytes, zbuf, (uint32_t)rem);
+        bulk_commit_group();
+    }
         if (E <= 32) {
             // E <= 32: a group of LPT = pow2ceil(E) lanes per token.  Every lane of the group runs the reference's
             // sequential online-softmax recurrence itself (gate.cuh:575-584; E <= 32 steps on broadcast smem reads, so the
