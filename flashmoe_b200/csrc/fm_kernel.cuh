@@ -68,7 +68,8 @@ constexpr int BAR_DISP_DONE = BAR_XROWS + 1;                          // this CT
 constexpr int BAR_PUB_FULL = BAR_DISP_DONE + 1;                       // epilogue warps -> publisher: tile's stores issued
 constexpr int BAR_PUB_EMPTY = BAR_PUB_FULL + 2;                       // publisher -> epilogue warps: slot consumed
 constexpr int BAR_WG = BAR_PUB_EMPTY + 2;                             // router: bulk-staged gate weights
-constexpr int NUM_BARS = BAR_WG + 2;                                  // 36 (one spare keeps the ring 16-byte aligned)
+constexpr int BAR_REMOTE = BAR_WG + 1;                                // dispatch, warp 2: staged rows for other ranks
+constexpr int NUM_BARS = BAR_REMOTE + 1;                              // 36 (keeps the ring 16-byte aligned)
 constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
@@ -733,58 +734,78 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     if (in_regs) asm volatile("bar.arrive 5, 288;" ::: "memory");   // done with the stage area
     asm volatile("bar.sync 3, 288;" ::: "memory");                  // every slot of this chunk (p.slot) is written
     {
-        // Remote rows.  Entries are examined 32 at a time (lane j: entry base + j; expert and slot from the routing tables
-        // in global memory), then copied a few rows per step so that every lane has sixteen 16-byte loads in flight.
-        const int vec_per_row = H >> 3;
-        const int ppl = (vec_per_row + 31) >> 5;                         // pieces per lane per row
-        const int U = ppl >= 16 ? 16 : (ppl > 4 ? 8 : 4);                 // pieces per lane per row and step
-        const int R = 16 / U;                                             // rows per step
-        const int n_ent = n_tok * k;
-        for (int base = 0; base < n_ent; base += 32) {
-            const int ent = base + lane;
-            bool valid = false;
-            unsigned long long my_src = 0ull, my_dst = 0ull;
-            if (ent < n_ent) {
-                const size_t gi = (size_t)t0 * k + ent;
-                const int e = p.topk_idx[gi];
-                const int owner = e / p.nLx;
-                const int sl = p.slot[gi];
-                valid = owner != p.rank && sl < p.EC;
-                if (valid) {
-                    my_src = reinterpret_cast<unsigned long long>(p.x + (size_t)(t0 + ent / k) * H);
-                    my_dst = reinterpret_cast<unsigned long long>(
-                        p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + sl) * H);
-                }
+        // Remote rows through the TMA engine (SM-issued peer stores reached only ~400 GB/s over NVLink, bulk stores ~600):
+        // a window of the epilogue staging area -- unused until this CTA's first tile is complete; its first 8 KiB hold the
+        // zero source of the output zero-fill -- is filled with a run of consecutive token rows of x (one bulk load), every
+        // kept (token, pick) pair of those tokens that belongs to another rank is one bulk store of a whole row to that
+        // rank's receive buffer, and when the engine has read the window the next run follows.  The link paces the stores.
+        uint8_t* win = smem + OFF_EPI + 8192;
+        const int win_bytes = NUM_EPI_WARPS * EPI_WARP_BYTES - 8192;
+        const int rows_win = max(1, win_bytes / row_bytes);
+        uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_REMOTE;
+        uint32_t rphase = 0;
+        const bool fits = row_bytes <= win_bytes;   // (d_model > 12288: rows go piecewise, below)
+        for (int tw = 0; tw < n_tok; tw += rows_win) {
+            const int rows = min(rows_win, n_tok - tw);
+            // does any pair of these tokens go to another rank?  (expert and slot from the routing tables in global memory)
+            bool mine = false;
+            for (int i = lane; i < rows * k; i += 32) {
+                const size_t gi = (size_t)(t0 + tw) * k + i;
+                const int owner = p.topk_idx[gi] / p.nLx;
+                mine |= owner != p.rank && p.slot[gi] < p.EC;
             }
-            unsigned int mask = __ballot_sync(0xffffffffu, valid);
-            while (mask != 0u) {
-                unsigned long long rs[4], rd[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const bool take = r < R && mask != 0u;
-                    const int l = take ? __ffs(mask) - 1 : 0;
-                    if (take) mask &= mask - 1u;
-                    rs[r] = __shfl_sync(0xffffffffu, my_src, l);
-                    rd[r] = __shfl_sync(0xffffffffu, my_dst, l);
-                    if (!take) { rs[r] = 0ull; rd[r] = 0ull; }
+            const unsigned int anyone = __ballot_sync(0xffffffffu, mine);
+            if (anyone == 0u) continue;
+            if (fits) {
+                if (lane == 0) {
+                    fence_proxy_async_smem();
+                    mbar_arrive_expect_tx(rbar, (uint32_t)(rows * row_bytes));
+                    bulk_load_1d(win, p.x + (size_t)(t0 + tw) * H, (uint32_t)(rows * row_bytes), rbar);
                 }
-                for (int c0 = 0; c0 < ppl; c0 += U) {   // (rows wider than 16 pieces per lane: several rounds)
-                    uint4 val[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int r = q / U, v = (c0 + q % U) * 32 + lane;
-                        const unsigned long long sp = r == 0 ? rs[0] : (r == 1 ? rs[1] : (r == 2 ? rs[2] : rs[3]));
-                        if (sp != 0ull && v < vec_per_row) val[q] = ld_global_nc_v4(reinterpret_cast<const uint4*>(sp) + v);
+                mbar_wait(rbar, rphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 903);
+                rphase ^= 1;
+                for (int i = lane; i < rows * k; i += 32) {
+                    const size_t gi = (size_t)(t0 + tw) * k + i;
+                    const int e = p.topk_idx[gi];
+                    const int owner = e / p.nLx;
+                    const int sl = p.slot[gi];
+                    if (owner != p.rank && sl < p.EC)
+                        bulk_store_1d(p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + sl) * H,
+                                      win + (size_t)(i / k) * row_bytes, (uint32_t)row_bytes);
+                }
+                bulk_commit_group();
+                bulk_wait_group_read0();   // the engine has read the window
+                __syncwarp();
+            } else {
+                // very wide rows: one token at a time, in window-sized pieces
+                for (int off = 0; off < row_bytes; off += win_bytes) {
+                    const int nb = min(win_bytes, row_bytes - off);
+                    if (lane == 0) {
+                        fence_proxy_async_smem();
+                        mbar_arrive_expect_tx(rbar, (uint32_t)nb);
+                        bulk_load_1d(win, reinterpret_cast<const uint8_t*>(p.x + (size_t)(t0 + tw) * H) + off, (uint32_t)nb, rbar);
                     }
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int r = q / U, v = (c0 + q % U) * 32 + lane;
-                        const unsigned long long dp = r == 0 ? rd[0] : (r == 1 ? rd[1] : (r == 2 ? rd[2] : rd[3]));
-                        if (dp != 0ull && v < vec_per_row) st_global_v4(reinterpret_cast<uint4*>(dp) + v, val[q]);
+                    mbar_wait(rbar, rphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 904);
+                    rphase ^= 1;
+                    for (int i = lane; i < k; i += 32) {
+                        const size_t gi = (size_t)(t0 + tw) * k + i;
+                        const int e = p.topk_idx[gi];
+                        const int owner = e / p.nLx;
+                        const int sl = p.slot[gi];
+                        if (owner != p.rank && sl < p.EC)
+                            bulk_store_1d(reinterpret_cast<uint8_t*>(p.peer_recv_x[owner] +
+                                              ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + sl) * H) + off,
+                                          win, (uint32_t)nb);
                     }
+                    bulk_commit_group();
+                    bulk_wait_group_read0();
+                    __syncwarp();
                 }
             }
         }
+        asm volatile("bar.arrive 7, 288;" ::: "memory");   // the staging area belongs to the epilogue warps from here
+        bulk_wait_group0();        // the rows have arrived on the other ranks ...
+        fence_proxy_async_all();   // ... and are ordered before the generic-proxy acknowledgements
     }
     __syncwarp();
     // the remote acknowledgements also tell the peers that this chunk's output rows are zeroed (TMA stores issued by warp 4
@@ -1304,6 +1325,8 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
+        if (ntiles == 0 && p.W > 1 && (p.phase_mask & 1u))   // the staging area served as warp 2's window for the remote rows
+            asm volatile("bar.sync 7, 288;" ::: "memory");
         const bool stamp_tile = ntiles < 16 && tid == EPI_WARP0 * 32;
         if (stamp_tile) trace_stamp(p, 64 + ntiles);
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * BLOCK_N;
@@ -1445,6 +1468,7 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
         mbar_init(&bars[BAR_XROWS], 1);
         mbar_init(&bars[BAR_DISP_DONE], 1);
         mbar_init(&bars[BAR_WG], 1);
+        mbar_init(&bars[BAR_REMOTE], 1);
         fence_mbar_init();
     }
     if (warp == 0 && (tid & 31) == 0) {
