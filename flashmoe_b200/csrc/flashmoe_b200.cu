@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -149,6 +150,10 @@ struct fm_ctx {
     bool gather = false;
     const void* cached_xg = nullptr;
     CUtensorMap tm_xg;
+    bool tc_gate = false;               // router logits on the tensor cores (E <= 256)
+    const void* cached_gx = nullptr;
+    const void* cached_gw = nullptr;
+    CUtensorMap tm_gx, tm_gw;
     unsigned int* pkt_done = nullptr;
     void* peer_base[FM_MAX_WORLD] = {};
     bool peer_opened[FM_MAX_WORLD] = {};
@@ -270,6 +275,20 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
         if ((rc = make_tmap(&c->tm_a0, x, (uint64_t)d.S, d.H, fm::BLOCK_M))) return rc;
         c->cached_x = x;
     }
+    if (c->tc_gate) {
+        // router on tensor cores: x as [S, H] in 32-row boxes, Wg_eff = the [H, E] tensor read flat as [E, H]
+        // (python_bindings.cu:93-99, moe.cuh:107-109) in boxes of E_pad rows (a CTA pair stages half each); rows past E
+        // read as zero
+        if (c->cached_gx != x) {
+            if ((rc = make_tmap(&c->tm_gx, x, (uint64_t)d.S, d.H, 32))) return rc;
+            c->cached_gx = x;
+        }
+        if (c->cached_gw != gate_w) {
+            const uint32_t e_pad = (uint32_t)((d.E + 15) / 16 * 16);
+            if ((rc = make_tmap(&c->tm_gw, gate_w, (uint64_t)d.E, d.H, c->pair ? e_pad / 2 : e_pad))) return rc;
+            c->cached_gw = gate_w;
+        }
+    }
     if (c->gather && c->cached_xg != x) {   // x as [S, H] with a {64, 1} box: rows are picked one by one (TMA gather4)
         if ((rc = make_tmap(&c->tm_xg, x, (uint64_t)d.S, d.H, 1))) return rc;
         c->cached_xg = x;
@@ -296,6 +315,8 @@ int launch(fm_ctx* c, const void* x, const void* gate_w, const void* expert_w, c
     memset(&p, 0, sizeof(p));
     p.tm_a0 = c->tm_a0; p.tm_b0 = c->tm_b0; p.tm_a1 = c->tm_a1; p.tm_b1 = c->tm_b1;
     if (c->gather) p.tm_xg = c->tm_xg;
+    if (c->tc_gate) { p.tm_gx = c->tm_gx; p.tm_gw = c->tm_gw; }
+    p.tc_gate = c->tc_gate ? 1 : 0;
     p.S = d.S; p.H = d.H; p.P = d.P; p.E = d.E; p.k = d.k; p.W = d.world; p.rank = d.rank; p.nLx = nLx;
     p.EC = d.EC; p.pEC = d.pEC; p.TCM = d.TCM; p.act = c->cfg.hidden_act;
     p.TN0 = c->TN0; p.TN1 = c->TN1; p.tpc = c->tpc; p.num_pkts = c->num_pkts; p.num_blocks = c->num_blocks;
@@ -456,6 +477,9 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         const char* f = getenv("FM_FUSED_COMBINE");
         ctx->fused = ((f != nullptr && *f) ? atoi(f) != 0 : true) && d.k <= 2;
         ctx->dense = d.E == 1 && world == 1 && env_int("FM_DENSE_E1", 1) != 0;
+        // router logits by tcgen05.mma instead of the CUDA-core GEMV (2*S*H*E flops: 4.3 GFLOP per rank at E = 128,
+        // d_model 2048, 8192 tokens -- ~0.2 ms on the CUDA cores); one accumulator holds <= 256 experts
+        ctx->tc_gate = !ctx->dense && d.E <= 256 && env_int("FM_TC_GATE", 1) != 0;
         // TMA gather4 of local rows for tiles claimed before their copies landed: correct, but off by default -- measured on
         // config B a gather tile takes 24 us instead of 6.6 (32 gather4 operations per k-block per CTA sustain only about
         // one per 90 clocks), which costs far more than the ~5 us earlier start buys (160 vs 144 us per forward)
@@ -543,17 +567,37 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
     std::vector<Unit> g1_units;
     for (const Unit& u : units) if (!u.local) g1_units.push_back(u);
     for (const Unit& u : units) if (u.local) g1_units.push_back(u);
-    int lag = env_int("FM_G1_LAG", (int)units.size());
-    if (lag < 1) lag = 1;
-    if (lag >= (int)units.size()) {
-        for (const Unit& u : units) push(0, u);
-        for (const Unit& u : g1_units) push(1, u);
-    } else {
+    // FM_G1_LAG: -1 (default) = the orders described here; n >= 1 = GEMM1 of a unit n units after its GEMM0.
+    //   one rank:    all GEMM0, then all GEMM1 (measured best on config B);
+    //   two ranks:   GEMM0 local, GEMM0 remote, GEMM1 remote, GEMM1 local (the remote rows land while the local packets
+    //                run; the local adds, which nobody else waits for, come last);
+    //   four+ ranks: GEMM0 local, GEMM1 local, then the remote units with GEMM1 one unit behind GEMM0 -- the local
+    //                packets are the only work available until the remote rows have crossed NVLink (~50 us at 8 GPUs),
+    //                and starting the remote units' GEMM1 early spreads the return traffic (reductions over NVLink at
+    //                ~350 GB/s per GPU, which would otherwise pile up behind the last tiles) over the whole phase.
+    const int lag = env_int("FM_G1_LAG", -1);
+    if (lag >= 1 && lag < (int)units.size()) {
         for (size_t i = 0; i < units.size(); ++i) {
             push(0, units[i]);
             if ((int)i >= lag) push(1, units[i - lag]);
         }
         for (size_t i = units.size() - lag; i < units.size(); ++i) push(1, units[i]);
+    } else if (world >= 4 && lag < 0) {
+        std::vector<Unit> loc, rem;
+        for (const Unit& u : units) (u.local ? loc : rem).push_back(u);
+        for (const Unit& u : loc) push(0, u);
+        for (const Unit& u : loc) push(1, u);
+        // remote units grouped by source rank (nLx units per source, or per source pair): GEMM1 one source behind GEMM0
+        const size_t per_src = xpair ? (size_t)nLx : (size_t)nLx;
+        for (size_t g0 = 0; g0 < rem.size(); g0 += per_src) {
+            for (size_t i = g0; i < std::min(g0 + per_src, rem.size()); ++i) push(0, rem[i]);
+            if (g0 >= per_src)
+                for (size_t i = g0 - per_src; i < g0; ++i) push(1, rem[i]);
+        }
+        for (size_t i = rem.size() >= per_src ? rem.size() - per_src : 0; i < rem.size(); ++i) push(1, rem[i]);
+    } else {
+        for (const Unit& u : units) push(0, u);
+        for (const Unit& u : g1_units) push(1, u);
     }
     ctx->num_blocks = (int)blocks.size();
     ctx->total_items = start;

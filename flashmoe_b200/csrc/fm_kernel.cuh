@@ -69,7 +69,10 @@ constexpr int BAR_PUB_FULL = BAR_DISP_DONE + 1;                       // epilogu
 constexpr int BAR_PUB_EMPTY = BAR_PUB_FULL + 2;                       // publisher -> epilogue warps: slot consumed
 constexpr int BAR_WG = BAR_PUB_EMPTY + 2;                             // router: bulk-staged gate weights
 constexpr int BAR_REMOTE = BAR_WG + 1;                                // dispatch, warp 2: staged rows for other ranks
-constexpr int NUM_BARS = BAR_REMOTE + 1;                              // 36 (keeps the ring 16-byte aligned)
+constexpr int BAR_GFULL = BAR_REMOTE + 1;                             // router GEMM on tensor cores: 2 stages full / empty,
+constexpr int BAR_GEMPTY = BAR_GFULL + 2;                             // accumulator complete
+constexpr int BAR_GACC = BAR_GEMPTY + 2;
+constexpr int NUM_BARS = BAR_GACC + 2;                                // 42 (one spare keeps the ring 16-byte aligned)
 constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
@@ -110,6 +113,9 @@ struct FmParams {
     CUtensorMap tm_a1;  // hidden  as [W*nLx*pEC, P]  box {64, 128}
     CUtensorMap tm_b1;  // expert_weights as [nLx*2*H, P]  box {64, 256}  (W_down rows)
     CUtensorMap tm_xg;  // x as [S, H], box {64, 1}: TMA gather4 of token rows for local packets (no dispatch copy needed)
+    CUtensorMap tm_gx;  // router on tensor cores: x as [S, H], box {64, 32}
+    CUtensorMap tm_gw;  // router on tensor cores: Wg_eff [E, H], box {64, E_pad} (CTA pair: {64, E_pad / 2})
+    int tc_gate;        // 1 = logits by tcgen05.mma (E <= 256); 0 = register-blocked CUDA-core GEMV
     int S, H, P, E, k, W, rank, nLx, EC, pEC, TCM, act;
     int TN0, TN1, tpc, num_pkts, num_blocks, total_items;
     int bn[2];          // tile width of GEMM0 / GEMM1 (128 or 256)
@@ -217,6 +223,90 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 //   Slots: ascending-token order within the CTA's chunk here; chunk bases after the grid barrier (a legal
 //   interleaving of the reference's BlockScan + atomicAdd(eC) order, gate.cuh:678-718).
 // ============================================================================================================
+// Router logits on the tensor cores (E <= 256): logits[t, e] = sum_h x[t,h] * Wg_eff[e,h] for one sub-chunk of <= 128 tokens
+// of this CTA as ONE tcgen05.mma accumulator: A = the tokens' x rows (TMA, 32-row boxes straight from x), B = Wg_eff padded
+// to a multiple of 16 experts (TMA; rows past E read as zero), D = [128 tokens x E_pad] fp32 in TMEM columns [0, E_pad).
+// A CTA pair runs it as cta_group::2 (M = 256: each CTA's own tokens; each CTA stages half of the Wg rows), because all
+// tcgen05 instructions of a kernel must use one cta_group; the two CTAs therefore walk the sub-chunks in lock-step.
+// Two smem stages in the router's weight scratch (one when E_pad > 128).  Afterwards warps 0-3 copy the accumulator to
+// the logits scratch (thread = token row), where the softmax / top-k code finds it exactly like after the GEMV.
+// The reference computes the same product with mma.sync tiles padded to 64 experts (gate.cuh:526-535); fp32 accumulation
+// order differs between the two (and from the oracle's), which is what the oracle's ambiguity flags are for.
+struct GateTcState { int gkb; uint32_t accphase; };
+template <bool PAIR>
+__device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem, int t0, int s0, int n_sub, int rows_span,
+                                               uint32_t crank, uint32_t tmem_base, float* logit_s, int ldl, GateTcState& st) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
+    uint64_t* gfull = bars + BAR_GFULL;
+    uint64_t* gempty = bars + BAR_GEMPTY;
+    uint64_t* gacc = bars + BAR_GACC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int E = p.E, E_pad = (E + 15) & ~15;
+    const int b_rows = PAIR ? E_pad / 2 : E_pad;                 // Wg_eff rows this CTA stages
+    const int b_bytes = b_rows * BLOCK_K * 2;
+    const int NS = 2 * (A_STAGE_BYTES + b_bytes) <= G_WG_BYTES ? 2 : 1;
+    const int stage_bytes = G_WG_BYTES / NS;
+    const int nk = p.H / BLOCK_K;
+    const int nb32 = (rows_span + 31) / 32;                      // 32-row boxes of x per k-block (same in both CTAs of a pair)
+    const uint32_t tx_cta = (uint32_t)(nb32 * 32 * BLOCK_K * 2 + b_bytes);
+    if (warp == 0 && lane == 0) {          // TMA issuer of this CTA
+        for (int kb = 0; kb < nk; ++kb) {
+            const int g = st.gkb + kb, s = g % NS;
+            const uint32_t ph = (uint32_t)(g / NS) & 1u;
+            mbar_wait(&gempty[s], ph ^ 1u, p.dbg, p.timeout_ns, FM_TRAP_MBAR_EMPTY, 910 + s);
+            uint8_t* sa = smem + G_OFF_WG + s * stage_bytes;
+            if (PAIR) {
+                if (crank == 0) mbar_arrive_expect_tx(&gfull[s], 2u * tx_cta);
+                const uint32_t leader_full = mapa_shared(smem_u32(&gfull[s]), 0);
+                for (int j = 0; j < nb32; ++j)
+                    tma_load_2d_pair(sa + j * 4096, &p.tm_gx, kb * BLOCK_K, t0 + s0 + j * 32, leader_full);
+                tma_load_2d_pair(sa + A_STAGE_BYTES, &p.tm_gw, kb * BLOCK_K, (int)crank * b_rows, leader_full);
+            } else {
+                mbar_arrive_expect_tx(&gfull[s], tx_cta);
+                for (int j = 0; j < nb32; ++j) tma_load_2d(sa + j * 4096, &p.tm_gx, kb * BLOCK_K, t0 + s0 + j * 32, &gfull[s]);
+                tma_load_2d(sa + A_STAGE_BYTES, &p.tm_gw, kb * BLOCK_K, 0, &gfull[s]);
+            }
+        }
+    } else if (warp == 1 && lane == 0 && crank == 0) {   // MMA issuer (leader CTA)
+        const uint32_t idesc = umma_idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, (uint32_t)E_pad);
+        for (int kb = 0; kb < nk; ++kb) {
+            const int g = st.gkb + kb, s = g % NS;
+            const uint32_t ph = (uint32_t)(g / NS) & 1u;
+            mbar_wait(&gfull[s], ph, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 910 + s);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + G_OFF_WG + s * stage_bytes);
+            const uint64_t da = umma_smem_desc_sw128(sa);
+            const uint64_t db = umma_smem_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                if (PAIR) umma_bf16_ss_pair(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+                else umma_bf16_ss(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            if (PAIR) umma_commit_pair(&gempty[s]); else umma_commit(&gempty[s]);
+        }
+        if (PAIR) umma_commit_pair(gacc); else umma_commit(gacc);
+    }
+    st.gkb += nk;
+    // accumulator complete (in a pair the commit is multicast to both CTAs' barriers)
+    mbar_wait(gacc, st.accphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, 911);
+    st.accphase ^= 1u;
+    tcgen05_fence_after();
+    if (warp < 4) {   // TMEM lanes [32w, 32w+32) = token rows; 16 columns (experts) per load
+        const int row = warp * 32 + lane;
+        for (int c0 = 0; c0 < E_pad; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_wait();
+            if (row < n_sub) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < E) logit_s[row * ldl + c0 + i] = __uint_as_float(v[i]);
+            }
+        }
+    }
+    tcgen05_fence_before();
+}
+
 // E == 1 (reference: the dense fffn kernel is selected instead of the MoE kernel, moe.cuh:174-177): every token goes to
 // expert 0 with probability 1, slot = token index, nothing is dropped (EC >= S).  No GEMV, no softmax.
 __device__ __forceinline__ void gate_phase_dense(const FmParams& p, int t0, int n_tok) {
@@ -239,7 +329,8 @@ __device__ __forceinline__ void gate_phase_dense(const FmParams& p, int t0, int 
     }
 }
 
-__device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok) {
+template <bool PAIR>
+__device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int t0, int n_tok, uint32_t crank) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int E = p.E, H = p.H, k = p.k;
     __nv_bfloat16* wg_s = reinterpret_cast<__nv_bfloat16*>(smem + G_OFF_WG);
@@ -258,10 +349,34 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
     if (Hc > H) Hc = H;
     const int ldl = E + 1;                                  // padded logits row (bank spread for thread-per-row)
     int TS = G_LOGIT_BYTES / (ldl * 4);                     // tokens per sub-chunk
-    if (TS > n_tok) TS = n_tok;
+    const bool tc = p.tc_gate != 0;
+    if (tc) TS = min(TS, BLOCK_M);                          // one tcgen05 accumulator = 128 token rows
+    else if (TS > n_tok) TS = n_tok;
+    // tensor-core logits: the two CTAs of a pair issue one cta_group::2 MMA per sub-chunk together, so both walk the same
+    // number of sub-chunks (tpc tokens) even if this CTA owns fewer tokens
+    const int span = tc ? p.tpc : n_tok;
+    GateTcState tcs;
+    tcs.gkb = 0; tcs.accphase = 0u;
+    uint32_t tmem_base = 0;
+    if (tc) {
+        // TMEM was allocated in the prologue by warp 2; in a pair the partner's barriers and TMEM must exist before the
+        // first remote completion / multicast commit (the grid barrier, which used to order that, comes later)
+        tcgen05_fence_before();
+        if (PAIR) cluster_sync_all(); else __syncthreads();
+        tcgen05_fence_after();
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM_PTR);
+    }
 
-    for (int s0 = 0; s0 < n_tok; s0 += TS) {
-        const int n_sub = min(TS, n_tok - s0);
+    for (int s0 = 0; s0 < span; s0 += TS) {
+        const int n_sub = max(0, min(TS, n_tok - s0));
+        if (tc) {
+            if (s0 > 0) {   // the accumulator columns and the logits scratch are reused: everybody is done with the previous ones
+                tcgen05_fence_before();
+                if (PAIR) cluster_sync_all(); else __syncthreads();
+                tcgen05_fence_after();
+            }
+            gate_logits_tc<PAIR>(p, smem, t0, s0, n_sub, min(TS, p.tpc - s0), crank, tmem_base, logit_s, ldl, tcs);
+        } else {
         for (int i = tid; i < n_sub * ldl; i += NUM_THREADS) logit_s[i] = 0.0f;
         for (int eg0 = 0; eg0 < E; eg0 += EG) {
             const int eg_len = min(EG, E - eg0);
@@ -363,6 +478,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 }
             }
         }
+        }   // GEMV path
         __syncthreads();
         if (tid == 0) trace_stamp(p, 11);
         if (p.fused && s0 == 0 && warp == EPI_WARP0) {
@@ -1469,6 +1585,8 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
         mbar_init(&bars[BAR_DISP_DONE], 1);
         mbar_init(&bars[BAR_WG], 1);
         mbar_init(&bars[BAR_REMOTE], 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars[BAR_GFULL + i], 1); mbar_init(&bars[BAR_GEMPTY + i], 1); }
+        mbar_init(&bars[BAR_GACC], 1);
         fence_mbar_init();
     }
     if (warp == 0 && (tid & 31) == 0) {
@@ -1495,7 +1613,7 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
                 for (int r = 0; r < bn_w; r += step) tma_prefetch_l2_2d(tb, kb * BLOCK_K, b0 + r);
         }
     }
-    if (warp == 2 && (p.phase_mask & 2u)) { if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
+    if (warp == 2 && ((p.phase_mask & 2u) || p.tc_gate)) { if (PAIR) tmem_alloc_pair(tmem_ptr, TMEM_COLS); else tmem_alloc(tmem_ptr, TMEM_COLS); }
     tcgen05_fence_before();
 }
 
@@ -1711,7 +1829,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
             }
             if (tid == 0) *p.claim = 0u;
         }
-        if (p.dense) gate_phase_dense(p, t0, n_tok); else gate_phase(p, smem, t0, n_tok);
+        if (p.dense) gate_phase_dense(p, t0, n_tok); else gate_phase<PAIR>(p, smem, t0, n_tok, crank);
         if (tid == 0) trace_stamp(p, 1);
         grid_barrier(p);   // also a cluster-wide sync: the partner CTA's barriers are initialised before any remote arrive
         if (tid == 0) trace_stamp(p, 2);
@@ -1734,6 +1852,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fm_moe_forward_kernel(const __
         if (tid == EPI_WARP0 * 32) trace_stamp(p, 4);
         ffn_roles<PAIR>(p, smem, crank);
         ffn_teardown<PAIR>(p, smem);
+    } else if (p.tc_gate && (p.phase_mask & 1u)) {
+        ffn_teardown<PAIR>(p, smem);   // (router-only debug launch: the tensor-core router allocated TMEM)
     }
 
     if (p.phase_mask & 4u) {

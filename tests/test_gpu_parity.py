@@ -204,6 +204,23 @@ def test_host_buffer_entry_point_equals_device_path():
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["small_drop", "ragged_dims", "E64_k4", "E128_k2"])
+def test_router_cuda_core_path(monkeypatch, name):
+    """The router's logits come from tcgen05.mma by default (E <= 256); FM_TC_GATE=0 selects the register-blocked
+    CUDA-core GEMV (the only path for E > 256), which must stay parity-green too."""
+    monkeypatch.setenv("FM_TC_GATE", "0")
+    cfg = CASES[name]
+    x, wg, we, _, _ = make_inputs(cfg, seed=400 + len(name))
+    _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
+
+
+def test_router_many_experts_general_path():
+    """E = 320 > 256: beyond one tensor-core accumulator, the CUDA-core router is used automatically."""
+    cfg = MoEConfig(num_experts=320, expert_top_k=2, sequence_len=1024, hidden_size=128, intermediate_size=128)
+    x, wg, we, _, _ = make_inputs(cfg, seed=71)
+    _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
+
+
 @pytest.mark.parametrize("fused", [1, 0])
 def test_relaunch_with_changing_inputs_every_launch_checked(monkeypatch, fused):
     """Back-to-back launches on ONE context with different activations (routing, per-expert counts and drops change,
@@ -213,7 +230,8 @@ def test_relaunch_with_changing_inputs_every_launch_checked(monkeypatch, fused):
     cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=1024, hidden_size=256, intermediate_size=512, drop_tokens=0)
     g = torch.Generator().manual_seed(77)
     xs = [torch.randn(1, cfg.S, cfg.H, generator=g).bfloat16() for _ in range(3)]
-    xs[1][:, : cfg.S // 2] = xs[1][:, :1]        # half of the tokens identical: two experts get most rows
+    # half of the tokens near-identical (token 0 + small noise): two experts get most rows
+    xs[1][:, : cfg.S // 2] = (xs[1][:, :1].float() + torch.randn(1, cfg.S // 2, cfg.H, generator=g) * 0.02).bfloat16()
     _, wg, we, _, _ = make_inputs(cfg, seed=78)
     refs = [run_oracle(cfg, x, wg, we) for x in xs]
     ctx = _ctx(cfg)
