@@ -479,7 +479,9 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
         ctx->dense = d.E == 1 && world == 1 && env_int("FM_DENSE_E1", 1) != 0;
         // router logits by tcgen05.mma instead of the CUDA-core GEMV (2*S*H*E flops: 4.3 GFLOP per rank at E = 128,
         // d_model 2048, 8192 tokens -- ~0.2 ms on the CUDA cores); one accumulator holds <= 256 experts
-        ctx->tc_gate = !ctx->dense && d.E <= 256 && env_int("FM_TC_GATE", 1) != 0;
+        // Default: from 17 experts up.  Measured on one B200: E = 128, d_model 2048, 56 tokens per CTA: router 29 us instead
+        // of 433 us; E = 8, d_model 1024, 28 tokens per CTA (config B): a wash (the GEMV is latency-, not flop-bound there).
+        ctx->tc_gate = !ctx->dense && d.E <= 256 && env_int("FM_TC_GATE", d.E > 16 ? 1 : 0) != 0;
         // TMA gather4 of local rows for tiles claimed before their copies landed: correct, but off by default -- measured on
         // config B a gather tile takes 24 us instead of 6.6 (32 gather4 operations per k-block per CTA sustain only about
         // one per 90 clocks), which costs far more than the ~5 us earlier start buys (160 vs 144 us per forward)

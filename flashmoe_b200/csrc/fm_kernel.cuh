@@ -69,10 +69,11 @@ constexpr int BAR_PUB_FULL = BAR_DISP_DONE + 1;                       // epilogu
 constexpr int BAR_PUB_EMPTY = BAR_PUB_FULL + 2;                       // publisher -> epilogue warps: slot consumed
 constexpr int BAR_WG = BAR_PUB_EMPTY + 2;                             // router: bulk-staged gate weights
 constexpr int BAR_REMOTE = BAR_WG + 1;                                // dispatch, warp 2: staged rows for other ranks
-constexpr int BAR_GFULL = BAR_REMOTE + 1;                             // router GEMM on tensor cores: 2 stages full / empty,
-constexpr int BAR_GEMPTY = BAR_GFULL + 2;                             // accumulator complete
-constexpr int BAR_GACC = BAR_GEMPTY + 2;
-constexpr int NUM_BARS = BAR_GACC + 2;                                // 42 (one spare keeps the ring 16-byte aligned)
+constexpr int GATE_STAGES = 8;                                        // router GEMM on tensor cores: up to 8 smem stages
+constexpr int BAR_GFULL = BAR_REMOTE + 1;                             // full / empty per stage, accumulator complete
+constexpr int BAR_GEMPTY = BAR_GFULL + GATE_STAGES;
+constexpr int BAR_GACC = BAR_GEMPTY + GATE_STAGES;
+constexpr int NUM_BARS = BAR_GACC + 2;                                // 54 (one spare keeps the ring 16-byte aligned)
 constexpr int OFF_RING = OFF_BARS + NUM_BARS * 8;                     // 16-byte aligned
 constexpr int OFF_TMEM_PTR = OFF_RING + NSCHED * 64;
 constexpr int OFF_MISC = OFF_TMEM_PTR + 16;
@@ -244,11 +245,16 @@ __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem,
     const int E = p.E, E_pad = (E + 15) & ~15;
     const int b_rows = PAIR ? E_pad / 2 : E_pad;                 // Wg_eff rows this CTA stages
     const int b_bytes = b_rows * BLOCK_K * 2;
-    const int NS = 2 * (A_STAGE_BYTES + b_bytes) <= G_WG_BYTES ? 2 : 1;
-    const int stage_bytes = G_WG_BYTES / NS;
     const int nk = p.H / BLOCK_K;
     const int nb32 = (rows_span + 31) / 32;                      // 32-row boxes of x per k-block (same in both CTAs of a pair)
-    const uint32_t tx_cta = (uint32_t)(nb32 * 32 * BLOCK_K * 2 + b_bytes);
+    const int a_bytes = nb32 * 32 * BLOCK_K * 2;                 // x rows actually staged; the MMA reads 128 rows from the stage
+                                                                 // base -- rows beyond a_bytes are whatever follows (their
+                                                                 // accumulator rows are never read)
+    const uint32_t tx_cta = (uint32_t)(a_bytes + b_bytes);
+    // stages live in the router's weight + logits scratch (the logits are written only after the last MMA of the
+    // sub-chunk has completed); compact stride = what is staged, so a 28-token chunk with 8 experts gets 8 stages of 5 KB
+    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+    const int NS = max(1, min(GATE_STAGES, (G_WG_BYTES + G_LOGIT_BYTES - (A_STAGE_BYTES - a_bytes)) / stage_bytes));
     if (warp == 0 && lane == 0) {          // TMA issuer of this CTA
         for (int kb = 0; kb < nk; ++kb) {
             const int g = st.gkb + kb, s = g % NS;
@@ -260,11 +266,11 @@ __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem,
                 const uint32_t leader_full = mapa_shared(smem_u32(&gfull[s]), 0);
                 for (int j = 0; j < nb32; ++j)
                     tma_load_2d_pair(sa + j * 4096, &p.tm_gx, kb * BLOCK_K, t0 + s0 + j * 32, leader_full);
-                tma_load_2d_pair(sa + A_STAGE_BYTES, &p.tm_gw, kb * BLOCK_K, (int)crank * b_rows, leader_full);
+                tma_load_2d_pair(sa + a_bytes, &p.tm_gw, kb * BLOCK_K, (int)crank * b_rows, leader_full);
             } else {
                 mbar_arrive_expect_tx(&gfull[s], tx_cta);
                 for (int j = 0; j < nb32; ++j) tma_load_2d(sa + j * 4096, &p.tm_gx, kb * BLOCK_K, t0 + s0 + j * 32, &gfull[s]);
-                tma_load_2d(sa + A_STAGE_BYTES, &p.tm_gw, kb * BLOCK_K, 0, &gfull[s]);
+                tma_load_2d(sa + a_bytes, &p.tm_gw, kb * BLOCK_K, 0, &gfull[s]);
             }
         }
     } else if (warp == 1 && lane == 0 && crank == 0) {   // MMA issuer (leader CTA)
@@ -276,7 +282,7 @@ __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem,
             tcgen05_fence_after();
             const uint32_t sa = smem_u32(smem + G_OFF_WG + s * stage_bytes);
             const uint64_t da = umma_smem_desc_sw128(sa);
-            const uint64_t db = umma_smem_desc_sw128(sa + A_STAGE_BYTES);
+            const uint64_t db = umma_smem_desc_sw128(sa + a_bytes);
 #pragma unroll
             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                 if (PAIR) umma_bf16_ss_pair(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
@@ -1585,7 +1591,7 @@ __device__ __forceinline__ void ffn_setup(const FmParams& p, uint8_t* smem) {
         mbar_init(&bars[BAR_DISP_DONE], 1);
         mbar_init(&bars[BAR_WG], 1);
         mbar_init(&bars[BAR_REMOTE], 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bars[BAR_GFULL + i], 1); mbar_init(&bars[BAR_GEMPTY + i], 1); }
+        for (int i = 0; i < GATE_STAGES; ++i) { mbar_init(&bars[BAR_GFULL + i], 1); mbar_init(&bars[BAR_GEMPTY + i], 1); }
         mbar_init(&bars[BAR_GACC], 1);
         fence_mbar_init();
     }

@@ -214,6 +214,16 @@ def test_router_cuda_core_path(monkeypatch, name):
     _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
 
 
+@pytest.mark.parametrize("name", ["tiny", "small_drop", "ragged_dims", "configA_top1", "multi_seq"])
+def test_router_tensor_core_path_small_expert_counts(monkeypatch, name):
+    """FM_TC_GATE=1 forces the tcgen05 router where the default (E <= 16) is the CUDA-core GEMV: padded expert columns
+    (E = 2, 4, 6, 8 -> 16), 8-row halves of Wg per CTA of a pair, chunks of fewer than 32 tokens."""
+    monkeypatch.setenv("FM_TC_GATE", "1")
+    cfg = CASES[name]
+    x, wg, we, _, _ = make_inputs(cfg, seed=500 + len(name))
+    _compare(cfg, _run(cfg, x, wg, we), run_oracle(cfg, x, wg, we))
+
+
 def test_router_many_experts_general_path():
     """E = 320 > 256: beyond one tensor-core accumulator, the CUDA-core router is used automatically."""
     cfg = MoEConfig(num_experts=320, expert_top_k=2, sequence_len=1024, hidden_size=128, intermediate_size=128)
