@@ -172,3 +172,18 @@ def test_aux_loss_restatement_against_a_numpy_computation():
     np.testing.assert_allclose(gmec, ref.counts / cfg.S, rtol=1e-7)
     np.testing.assert_allclose(loss, float((p.mean(axis=0) * ref.counts / cfg.S).sum() / cfg.E), rtol=1e-5)
     assert abs(gml.sum() - 1.0) < 1e-5 and abs(gmec.sum() - cfg.k) < 1e-6
+
+
+def test_sampled_forward_equals_full_forward_on_the_sample():
+    """fmo_forward_sample (bench.py's post-run parity check, full-size multi-GPU parity): routing / slots / drops over all
+    tokens, FFN + combine only for the sample -- bit-identical to the full forward on those tokens, duplicates allowed."""
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=512, hidden_size=256, intermediate_size=512)
+    x, wg, we, _, _ = make_inputs(cfg, seed=3)
+    ref = run_oracle(cfg, x, wg, we)
+    up, down = mo.split_expert_weights(mo.to_bits(we))
+    sample = np.array([5, 0, 511, 77, 300, 300], dtype=np.int32)
+    r = mo.forward_sample(mo.to_bits(x.reshape(cfg.S, cfg.H)), mo.gate_weights_effective(mo.to_bits(wg), cfg.E, cfg.H), up, down,
+                          sample, k=cfg.k, EC=cfg.EC)
+    assert (r.out == ref.out[sample]).all()
+    assert (r.topk_idx == ref.topk_idx).all() and (r.slot == ref.slot).all() and (r.counts == ref.counts).all()
+    assert (r.kept == ref.kept).all() and (r.ambiguous == ref.ambiguous).all()
