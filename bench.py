@@ -442,8 +442,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="B", choices=sorted(BASELINE_CONFIGS))
-    ap.add_argument("--sweeps", default=os.environ.get("FM_BENCH_SWEEPS", ""),
-                    help="comma-separated extra configs measured with reduced steps and appended as \"sweeps\"")
+    ap.add_argument("--sweeps", default=os.environ.get("FM_BENCH_SWEEPS"),
+                    help="comma-separated extra configs measured with reduced steps and appended as \"sweeps\" (default: the "
+                         "BASELINE.json multi-GPU configs at 8 GPUs -- C, the token sweep, the expert sweep -- the expert sweep "
+                         "at 4 GPUs, none otherwise; 'none' disables)")
     ap.add_argument("--sweep-steps", type=int, default=20)
     ap.add_argument("--parity-tokens", type=int, default=int(os.environ.get("FM_BENCH_PARITY_TOKENS", "256")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -509,7 +511,9 @@ def main():
     if "parity" in res:
         line["parity_check"] = res["parity"]
 
-    sweeps = [s for s in args.sweeps.split(",") if s]
+    if args.sweeps is None:   # BASELINE.json: configs[2..4] are quoted on 8 (and 4) GPUs
+        args.sweeps = {8: "C,D1k,D4k,D16k,D64k,E8,E16,E32,E64,E128", 4: "E8,E16,E32,E64,E128"}.get(world, "")
+    sweeps = [s for s in args.sweeps.split(",") if s and s != "none"]
     if sweeps:
         line["sweeps"] = []
         t_budget = time.perf_counter() + float(os.environ.get("FM_BENCH_SWEEP_BUDGET_S", "240"))
