@@ -557,6 +557,62 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 __syncwarp();
                 if (own && valid) logit_s[ti * ldl + sub] = pe;   // probabilities (training-mode column sums read them)
             }
+        } else if (E <= 1024) {
+            // 32 < E <= 1024: the same scheme with C = ceil(E / LPT) <= 32 experts per lane (lane `sub` owns experts sub,
+            // sub + LPT, ...): 8 / 4 / 2 / 1 tokens per warp.  (A thread per token leaves one or two warps of the CTA doing
+            // ~5 E dependent steps each: 17 us at E = 128 with 56 tokens.)  Every lane of a group runs the sequential
+            // recurrence itself; a lane scans its own experts in ascending order with a strict '>', the group reduction
+            // prefers the larger value and, on equal values, the lower index -- together the reference's ascending scan.
+            const int LPT = E <= 128 ? 4 : E <= 256 ? 8 : E <= 512 ? 16 : 32;
+            const int TPW = 32 / LPT, sub = lane & (LPT - 1);
+            for (int tb = warp * TPW; tb < n_sub; tb += NUM_WARPS * TPW) {
+                const int ti_raw = tb + lane / LPT;
+                const bool valid = ti_raw < n_sub;
+                const int ti = valid ? ti_raw : n_sub - 1;   // (idle groups compute on a copy of the last row, write nothing)
+                float* l = logit_s + ti * ldl;
+                const int t = t0 + s0 + ti;
+                float dI = 0.0f, mI = -INFINITY;
+                for (int e = 0; e < E; ++e) {
+                    const float pM = mI;
+                    mI = fmaxf(mI, l[e]);
+                    dI = fmaf(dI, fast_expf(pM - mI), fast_expf(l[e] - mI));
+                }
+                __syncwarp();   // every lane of the group has read the logits before they are replaced by probabilities
+                if (valid)
+                    for (int e = sub; e < E; e += LPT) {
+                        const float pe = __fdividef(fast_expf(l[e] - mI), dI);
+                        l[e] = pe;
+                        p.gate_out[(size_t)t * E + e] = __float2bfloat16_rn(pe);
+                    }
+                unsigned int taken = 0u;
+                float sum = 0.0f;
+                for (int i = 0; i < k; ++i) {
+                    float bv = -INFINITY;
+                    int bi = 0x7fffffff;
+                    if (valid) {
+                        int c = 0;
+                        for (int e = sub; e < E; e += LPT, ++c) {
+                            const float v = l[e];
+                            if (v > bv && !((taken >> c) & 1u)) { bv = v; bi = e; }
+                        }
+                    }
+                    for (int off = LPT >> 1; off >= 1; off >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                    }
+                    if (bi == 0x7fffffff) { bi = 0; }   // nothing comparable left (NaN logits): the thread-per-token form's default
+                    if ((bi & (LPT - 1)) == sub) taken |= 1u << (bi / LPT);
+                    sum += bv;
+                    if (sub == 0 && valid) {
+                        p.topk_idx[(size_t)t * k + i] = bi;
+                        p.topk_w[(size_t)t * k + i] = __float2bfloat16_rn(bv);
+                        sel_e[(s0 + ti) * k + i] = (int16_t)bi;
+                    }
+                }
+                if (sub == 0 && valid) p.mcw[t] = sum;
+                __syncwarp();
+            }
         } else
         // thread-per-token softmax + top-k, the same per-thread recurrence the reference runs after its transpose
         for (int ti = tid; ti < n_sub; ti += NUM_THREADS) {
@@ -682,7 +738,37 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     // one pass over chunk_counts [G, E] gives the prefix (lower chunks), this chunk's own counts and the totals
     for (int e = tid; e < E; e += DISP_THREADS) { base_s[e] = 0; total_s[e] = 0; }
     disp_sync();
-    {
+    const int E4 = E >> 2;
+    if ((E & 3) == 0 && E4 <= DISP_THREADS && (DISP_THREADS % E4) == 0) {
+        // 16-byte loads, four experts at a time; a thread always meets the same four (DISP_THREADS is a multiple of E / 4),
+        // so it sums in registers and touches shared memory once.  (E = 128: 2 batches of loads instead of 9.)
+        const int nb4 = (int)blockIdx.x * E4, n4 = G * E4;
+        int pt[4] = {0, 0, 0, 0}, pb[4] = {0, 0, 0, 0};
+        for (int i0 = tid; i0 < n4; i0 += 8 * DISP_THREADS) {
+            int4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * DISP_THREADS;
+                v[u] = i < n4 ? ld_global_cg_i4(reinterpret_cast<const int4*>(p.chunk_counts) + i) : make_int4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * DISP_THREADS;
+                if (i >= n4) break;
+                if (i >= nb4 && i < nb4 + E4) *reinterpret_cast<int4*>(own_s + 4 * (i - nb4)) = v[u];
+                pt[0] += v[u].x; pt[1] += v[u].y; pt[2] += v[u].z; pt[3] += v[u].w;
+                if (i < nb4) { pb[0] += v[u].x; pb[1] += v[u].y; pb[2] += v[u].z; pb[3] += v[u].w; }
+            }
+        }
+        if (tid < n4) {
+            const int e0 = 4 * (tid % E4);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (pt[q] != 0) atomicAdd(&total_s[e0 + q], pt[q]);
+                if (pb[q] != 0) atomicAdd(&base_s[e0 + q], pb[q]);
+            }
+        }
+    } else {
         const int nb = (int)blockIdx.x * E, n = G * E;
         const bool fixed_e = (E <= DISP_THREADS) && (DISP_THREADS % E) == 0;   // then a thread always meets one e
         int part_b = 0, part_t = 0, cur_e = -1;
