@@ -847,13 +847,10 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
     //     (token, pick) pair is one cp.async.bulk store of a whole row through the TMA engine (no per-lane chains).  They
     //     land in ~4 us and are acknowledged at once (gpu-scope release); the stage area is handed to the TMA producer, the
     //     warps become epilogue warps, and the expert FFN starts on the local packets while
-    //   * rows for experts on OTHER ranks (warp 2) leave from the same staged rows as bulk stores to the owners' receive
-    //     buffers over NVLink, all of a group in flight at once.  (Measured alternatives: SM-issued 16-byte peer stores
-    //     stall the issuing warps and reach ~350-400 GB/s; bulk stores through a small re-filled window serialise one
-    //     link round trip (~9 us) per window -- 28 us for three windows; from the full staging the remote rows are on
-    //     the other GPUs after roughly one round trip.)  The stage area goes to the TMA producer when the engine has read
-    //     the rows; warp 2 then waits for the stores' completion with a system-scope release and acknowledges them -- it
-    //     has no other duty until the first tile needs publishing.
+    //   * rows for experts on OTHER ranks (warp 2, from the moment the slots are known) cross NVLink as 16-byte peer stores
+    //     read straight from x (L2 hits), sixteen pieces per lane in flight.  The link bounds them (S*k*(1-1/W)*H*2 bytes
+    //     at ~770 GB/s) and back-pressures the issuing warp -- which has no other duty until the first tile needs
+    //     publishing; it then waits for the stores with a system-scope release and acknowledges them.
     uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_XROWS;   // initialised in the kernel prologue
     uint8_t* x_s = smem;   // the router's Wg / logits scratch is free now
     const int row_bytes = H * 2;
@@ -873,12 +870,10 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         }
     };
     constexpr int LOCAL_THREADS = DISP_THREADS - 32;   // warps 4..11
-    constexpr int RMAX = 8;   // remote experts per lane of warp 2 kept in registers (E <= 256)
-    const bool in_regs = E <= 32 * RMAX;
-    uint32_t xphase = 0;
     if (warp != 2) {
         // ---------------------------------------------------------------- warps 4-11: slots, routing records, local rows
         const int ltid = tid - 32;
+        uint32_t xphase = 0;
         for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
             const int rows = min(rows_per_group, n_tok - g0);
             if (ltid == 0 && g0 > 0) {   // group 0 was requested at the end of the router (gate_phase)
@@ -911,49 +906,31 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
             bulk_commit_group();
             if (g0 + rows_per_group < n_tok) {   // the staging buffer is reused: wait until the bulk stores have read it
                 bulk_wait_group_read0();
-                if (any_remote) disp_sync(); else asm volatile("bar.sync 4, 256;" ::: "memory");   // (warp 2 reads it, too)
+                asm volatile("bar.sync 4, 256;" ::: "memory");
             }
         }
+        if (any_remote) asm volatile("bar.arrive 3, 288;" ::: "memory");   // every slot (p.slot) is written: warp 2 may start
         bulk_wait_group0();        // this thread's local row stores (and warp 4's zero-fill stores) are complete ...
         fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
         asm volatile("bar.sync 4, 256;" ::: "memory");
-        if (any_remote) asm volatile("bar.arrive 6, 288;" ::: "memory");   // local rows, records, zero-fill complete (see warp 2)
+        if (any_remote) asm volatile("bar.arrive 6, 288;" ::: "memory");   // local rows + zero-fill complete (warp 2's acks wait for this)
         if (ltid == 0) trace_stamp(p, 9);
-        if (ltid < 32) {   // warp 4: acknowledge the local experts ...
+        if (any_remote) asm volatile("bar.sync 5, 288;" ::: "memory");   // warp 2 has taken what it needs from the stage area
+        if (ltid < 32) {   // warp 4: acknowledge the local experts, then hand the stage area to the TMA producer
             for (int e = first_local + ltid; e < first_local + p.nLx; e += 32) ack(e, base_s[e], min(base_s[e] + own_s[e], p.EC), true);
             __syncwarp();
+            // (more than 256 experts on several ranks: warp 2 still needs base / own for its acknowledgements and releases)
+            if (ltid == 0 && (!any_remote || E <= 256)) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
         }
-        // ... and, once warp 2's bulk stores have read the staged rows too, hand the stage area to the TMA producer
-        if (any_remote) asm volatile("bar.sync 5, 288;" ::: "memory");
-        if (ltid == 0 && (!any_remote || in_regs)) mbar_arrive(reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_DISP_DONE);
         return;
     }
-    // -------------------------------------------------------------------- warp 2: rows for experts on other ranks
+    // -------------------------------------------------------------------- warp 2
     if (!any_remote) return;
-    for (int g0 = 0; g0 < n_tok; g0 += rows_per_group) {
-        const int rows = min(rows_per_group, n_tok - g0);
-        mbar_wait(xbar, xphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 905);   // the same staged rows warps 4-11 use
-        xphase ^= 1;
-        for (int i = lane; i < rows * k; i += 32) {
-            const int tl = i / k, j = i - tl * k;
-            const int ti = g0 + tl;
-            const int e = sel_e[ti * k + j];
-            const int owner = e / p.nLx;
-            if (owner == p.rank) continue;
-            const int s = base_s[e] + rank_s[ti * k + j];
-            if (s < p.EC)
-                bulk_store_1d(p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + s) * H,
-                              x_s + (size_t)tl * row_bytes, (uint32_t)row_bytes);
-        }
-        bulk_commit_group();
-        if (g0 + rows_per_group < n_tok) {
-            bulk_wait_group_read0();
-            disp_sync();
-        }
-    }
     // the slot ranges of the remote experts go into registers (E <= 256) before the stage area -- where base / own live --
-    // is released; beyond that the release waits for the acknowledgements
+    // is released by warp 4; beyond that the release waits for this warp
+    constexpr int RMAX = 8;
     int rlo[RMAX], rhi[RMAX];
+    const bool in_regs = E <= 32 * RMAX;
 #pragma unroll
     for (int i = 0; i < RMAX; ++i) {
         const int e = lane + 32 * i;
@@ -961,13 +938,86 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         rlo[i] = remote ? base_s[e] : 0;
         rhi[i] = remote ? min(base_s[e] + own_s[e], p.EC) : 0;
     }
-    bulk_wait_group_read0();   // the engine has read the staged rows of this warp's stores
     __syncwarp();
     if (in_regs) asm volatile("bar.arrive 5, 288;" ::: "memory");   // done with the stage area
-    bulk_wait_group0();        // the rows have arrived on the other ranks ...
-    fence_proxy_async_all();   // ... and are ordered before the generic-proxy acknowledgements
+    asm volatile("bar.sync 3, 288;" ::: "memory");                  // every slot of this chunk (p.slot) is written
+    {
+        // Remote rows through the TMA engine (SM-issued peer stores reached only ~400 GB/s over NVLink, bulk stores ~600):
+        // a window of the epilogue staging area -- unused until this CTA's first tile is complete; its first 8 KiB hold the
+        // zero source of the output zero-fill -- is filled with a run of consecutive token rows of x (one bulk load), every
+        // kept (token, pick) pair of those tokens that belongs to another rank is one bulk store of a whole row to that
+        // rank's receive buffer, and when the engine has read the window the next run follows.  The link paces the stores.
+        uint8_t* win = smem + OFF_EPI + 8192;
+        const int win_bytes = NUM_EPI_WARPS * EPI_WARP_BYTES - 8192;
+        const int rows_win = max(1, win_bytes / row_bytes);
+        uint64_t* rbar = reinterpret_cast<uint64_t*>(smem + OFF_BARS) + BAR_REMOTE;
+        uint32_t rphase = 0;
+        const bool fits = row_bytes <= win_bytes;   // (d_model > 12288: rows go piecewise, below)
+        for (int tw = 0; tw < n_tok; tw += rows_win) {
+            const int rows = min(rows_win, n_tok - tw);
+            // does any pair of these tokens go to another rank?  (expert and slot from the routing tables in global memory)
+            bool mine = false;
+            for (int i = lane; i < rows * k; i += 32) {
+                const size_t gi = (size_t)(t0 + tw) * k + i;
+                const int owner = p.topk_idx[gi] / p.nLx;
+                mine |= owner != p.rank && p.slot[gi] < p.EC;
+            }
+            const unsigned int anyone = __ballot_sync(0xffffffffu, mine);
+            if (anyone == 0u) continue;
+            if (fits) {
+                if (lane == 0) {
+                    fence_proxy_async_smem();
+                    mbar_arrive_expect_tx(rbar, (uint32_t)(rows * row_bytes));
+                    bulk_load_1d(win, p.x + (size_t)(t0 + tw) * H, (uint32_t)(rows * row_bytes), rbar);
+                }
+                mbar_wait(rbar, rphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 903);
+                rphase ^= 1;
+                for (int i = lane; i < rows * k; i += 32) {
+                    const size_t gi = (size_t)(t0 + tw) * k + i;
+                    const int e = p.topk_idx[gi];
+                    const int owner = e / p.nLx;
+                    const int sl = p.slot[gi];
+                    if (owner != p.rank && sl < p.EC)
+                        bulk_store_1d(p.peer_recv_x[owner] + ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + sl) * H,
+                                      win + (size_t)(i / k) * row_bytes, (uint32_t)row_bytes);
+                }
+                bulk_commit_group();
+                bulk_wait_group_read0();   // the engine has read the window
+                __syncwarp();
+            } else {
+                // very wide rows: one token at a time, in window-sized pieces
+                for (int off = 0; off < row_bytes; off += win_bytes) {
+                    const int nb = min(win_bytes, row_bytes - off);
+                    if (lane == 0) {
+                        fence_proxy_async_smem();
+                        mbar_arrive_expect_tx(rbar, (uint32_t)nb);
+                        bulk_load_1d(win, reinterpret_cast<const uint8_t*>(p.x + (size_t)(t0 + tw) * H) + off, (uint32_t)nb, rbar);
+                    }
+                    mbar_wait(rbar, rphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_FULL, 904);
+                    rphase ^= 1;
+                    for (int i = lane; i < k; i += 32) {
+                        const size_t gi = (size_t)(t0 + tw) * k + i;
+                        const int e = p.topk_idx[gi];
+                        const int owner = e / p.nLx;
+                        const int sl = p.slot[gi];
+                        if (owner != p.rank && sl < p.EC)
+                            bulk_store_1d(reinterpret_cast<uint8_t*>(p.peer_recv_x[owner] +
+                                              ((size_t)(p.rank * p.nLx + (e - owner * p.nLx)) * p.pEC + sl) * H) + off,
+                                          win, (uint32_t)nb);
+                    }
+                    bulk_commit_group();
+                    bulk_wait_group_read0();
+                    __syncwarp();
+                }
+            }
+        }
+        asm volatile("bar.arrive 7, 288;" ::: "memory");   // the staging area belongs to the epilogue warps from here
+        bulk_wait_group0();        // the rows have arrived on the other ranks ...
+        fence_proxy_async_all();   // ... and are ordered before the generic-proxy acknowledgements
+    }
+    __syncwarp();
     // the remote acknowledgements also tell the peers that this chunk's output rows are zeroed (TMA stores issued by warp 4
-    // in the router) and that the routing records (written by warps 4-11) are out
+    // in the router, completed before it arrives here) and that the routing records are written
     asm volatile("bar.sync 6, 288;" ::: "memory");
     if (in_regs) {
 #pragma unroll
@@ -1483,6 +1533,8 @@ __device__ __forceinline__ void ffn_epilogue(const FmParams& p, uint8_t* smem, u
 
         mbar_wait(&tmem_full[as], aphase, p.dbg, p.timeout_ns, FM_TRAP_MBAR_TMEM_FULL, as);
         tcgen05_fence_after();
+        if (ntiles == 0 && p.W > 1 && (p.phase_mask & 1u))   // the staging area served as warp 2's window for the remote rows
+            asm volatile("bar.sync 7, 288;" ::: "memory");
         const bool stamp_tile = ntiles < 16 && tid == EPI_WARP0 * 32;
         if (stamp_tile) trace_stamp(p, 64 + ntiles);
         const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * BLOCK_N;
