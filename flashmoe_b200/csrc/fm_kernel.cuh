@@ -509,9 +509,10 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             for (int i = lane; i < n_tok; i += 32)
                 bulk_store_1d(reinterpret_cast<uint8_t*>(p.out_acc + (size_t)(t0 + i) * H) + (size_t)pieces * zbytes, zbuf, (uint32_t)rem);
         bulk_commit_group();
+        if (lane == 0) trace_stamp(p, 10);
     }
-        if (E <= 32) {
-            // E <= 32: a group of LPT = pow2ceil(E) lanes per token.  Every lane of the group runs the reference's
+        if (E <= 8) {
+            // E <= 8: a group of LPT = pow2ceil(E) lanes per token.  Every lane of the group runs the reference's
             // sequential online-softmax recurrence itself (gate.cuh:575-584; E <= 32 steps on broadcast smem reads, so the
             // result is bit-identical to the thread-per-row form), then lane `sub` owns expert `sub`: its probability,
             // the coalesced gateOut store, and its candidate in the k rounds of argmax -- a shuffle reduction that
@@ -558,9 +559,11 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 if (own && valid) logit_s[ti * ldl + sub] = pe;   // probabilities (training-mode column sums read them)
             }
         } else if (E <= 1024) {
-            // 32 < E <= 1024: the same scheme with C = ceil(E / LPT) <= 32 experts per lane (lane `sub` owns experts sub,
-            // sub + LPT, ...): 8 / 4 / 2 / 1 tokens per warp.  (A thread per token leaves one or two warps of the CTA doing
-            // ~5 E dependent steps each: 17 us at E = 128 with 56 tokens.)  Every lane of a group runs the sequential
+            // 8 < E <= 1024: the same scheme with C = ceil(E / LPT) <= 32 experts per lane (lane `sub` owns experts sub,
+            // sub + LPT, ...): 8 / 4 / 2 / 1 tokens per warp, so that a sub-chunk of up to 96 tokens is one round of the CTA's
+            // 12 warps (the recurrence is a dependent chain of E steps per token whatever the lane count; one lane per
+            // expert would serialise 111 tokens of the 16k-token sweep point into 10 rounds, a thread per token leaves one
+            // or two warps doing ~5 E dependent steps each: 17 us at E = 128 with 56 tokens).  Every lane of a group runs the sequential
             // recurrence itself; a lane scans its own experts in ascending order with a strict '>', the group reduction
             // prefers the larger value and, on equal values, the lower index -- together the reference's ascending scan.
             const int LPT = E <= 128 ? 4 : E <= 256 ? 8 : E <= 512 ? 16 : 32;
@@ -655,6 +658,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
             }
             p.mcw[t] = sum;
         }
+        if (tid == 0) trace_stamp(p, 15);
         __syncthreads();
         if (p.aux != nullptr) {
             // column sums of the fp32 probabilities of this sub-chunk (the reference block-reduces each gate tile's

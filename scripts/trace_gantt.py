@@ -21,7 +21,7 @@ def analyse(tr, cfg, label=""):
     tr = tr.astype(np.int64)
     t00 = tr[:, 0].min()
     us = lambda a: (a - t00) / 1e3  # noqa: E731
-    names = {0: "start", 11: "gate_gemv", 12: "gate_topk", 1: "gate_done", 2: "barrier", 8: "disp_prefix", 9: "disp_rows_done",
+    names = {0: "start", 11: "gate_gemv", 10: "zero_issued", 15: "topk_warp0", 12: "gate_topk", 1: "gate_done", 2: "barrier", 8: "disp_prefix", 9: "disp_rows_done",
              3: "dispatch_end", 4: "ffn_start", 5: "ffn_end", 6: "kernel_end"}
     print(f"--- {label} phases (us after the first CTA's start; min / median / max over CTAs)")
     for i, nm in names.items():
@@ -66,6 +66,10 @@ def analyse(tr, cfg, label=""):
                       ):
             v = v[np.isfinite(v)]
             print(f"    {nm:62s} med {np.median(v):7.2f}  p10 {np.percentile(v, 10):7.2f}  p90 {np.percentile(v, 90):7.2f}")
+    t0rows = [r for r in rows if r["i"] == 0]
+    if t0rows:
+        g = lambda key: np.median([(r[key] - t00) / 1e3 for r in t0rows])  # noqa: E731
+        print(f"  per pair, first tile: claimed {g('claim'):.1f}, rows ready {g('ready'):.1f}, first k-block landed {g('first'):.1f} us (medians)")
     # tensor-busy fraction per pair over the FFN phase (first 16 tiles only are stamped; config B has <= 10 per pair)
     busy = {}
     for r in rows:
