@@ -584,7 +584,7 @@ FM_API int fm_create(const fm_config_t* cfg, int rank, int world, int device, fm
             if ((int)i >= lag) push(1, units[i - lag]);
         }
         for (size_t i = units.size() - lag; i < units.size(); ++i) push(1, units[i]);
-    } else if (world >= 4 && lag < 0) {
+    } else if (world >= 4 && lag < 0 && env_int("FM_LOCAL_FIRST", 1) != 0) {   // (0: the two-rank order, for A/B runs)
         std::vector<Unit> loc, rem;
         for (const Unit& u : units) (u.local ? loc : rem).push_back(u);
         for (const Unit& u : loc) push(0, u);

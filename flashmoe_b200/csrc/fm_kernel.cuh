@@ -487,14 +487,15 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
         }   // GEMV path
         __syncthreads();
         if (tid == 0) trace_stamp(p, 11);
-        if (p.fused && s0 == 0 && warp == EPI_WARP0) {
+        if (p.fused && s0 == 0 && warp == NUM_WARPS - 1) {
         // The accumulation rows of this chunk's tokens start at zero (reference clearState zeroes the output,
         // moe.cuh:43-48).  Done by the TMA engine from a zeroed piece of the (still unused) epilogue staging area, so no
         // thread stalls on a store queue (as plain stores this cost 1.5-3 us on the router's critical path wherever it was
         // placed), and issued only now, after the GEMV: the engine works in order, and at the start of the kernel these
-        // stores sat in front of the gate-weight load (+5 us).  Warp 4 issues them here and waits for them in
-        // dispatch_phase before the local rows are acknowledged -- an expert only adds into a token's row after an
-        // acknowledgement of this CTA.
+        // stores sat in front of the gate-weight load (+5 us).  The LAST warp issues them (the softmax / top-k rounds below
+        // fill the warps from 0 upwards: with config B's 28 tokens per CTA warps 7-11 have none, and as warp 4's job
+        // the 3 us of this block were on the router's critical path) and waits for them in dispatch_phase before the
+        // local rows are acknowledged -- an expert only adds into a token's row after an acknowledgement of this CTA.
         uint8_t* zbuf = smem + OFF_EPI;
         const int row_bytes = H * 2, zbytes = min(row_bytes, 8192);
         for (int i = lane * 16; i < zbytes; i += 512) *reinterpret_cast<uint4*>(zbuf + i) = make_uint4(0u, 0u, 0u, 0u);
@@ -528,6 +529,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 const float* l = logit_s + ti * ldl;
                 const int t = t0 + s0 + ti;
                 float dI = 0.0f, mI = -INFINITY;
+#pragma unroll 8
                 for (int e = 0; e < E; ++e) {
                     const float pM = mI;
                     mI = fmaxf(mI, l[e]);
@@ -575,6 +577,9 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 float* l = logit_s + ti * ldl;
                 const int t = t0 + s0 + ti;
                 float dI = 0.0f, mI = -INFINITY;
+                // (unrolled so that the loads, the running maxima and the exponentials of 8 steps are in flight together;
+                // the dependent chain is then one max and one fma per step -- same operations in the same order)
+#pragma unroll 8
                 for (int e = 0; e < E; ++e) {
                     const float pM = mI;
                     mI = fmaxf(mI, l[e]);
@@ -582,6 +587,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 }
                 __syncwarp();   // every lane of the group has read the logits before they are replaced by probabilities
                 if (valid)
+#pragma unroll 4
                     for (int e = sub; e < E; e += LPT) {
                         const float pe = __fdividef(fast_expf(l[e] - mI), dI);
                         l[e] = pe;
@@ -594,6 +600,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                     int bi = 0x7fffffff;
                     if (valid) {
                         int c = 0;
+#pragma unroll 4
                         for (int e = sub; e < E; e += LPT, ++c) {
                             const float v = l[e];
                             if (v > bv && !((taken >> c) & 1u)) { bv = v; bi = e; }
@@ -913,8 +920,11 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
                 asm volatile("bar.sync 4, 256;" ::: "memory");
             }
         }
+        // (the zero-fill stores, an older bulk group of warp 11, read the first 8 KiB of the epilogue staging area, which
+        // is warp 2's window: they must have been read before warp 2 starts -- all but the newest group, the row stores)
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         if (any_remote) asm volatile("bar.arrive 3, 288;" ::: "memory");   // every slot (p.slot) is written: warp 2 may start
-        bulk_wait_group0();        // this thread's local row stores (and warp 4's zero-fill stores) are complete ...
+        bulk_wait_group0();        // this thread's local row stores (and warp 11's zero-fill stores) are complete ...
         fence_proxy_async_all();   // ... and ordered (async proxy) before the generic-proxy counter traffic below
         asm volatile("bar.sync 4, 256;" ::: "memory");
         if (any_remote) asm volatile("bar.arrive 6, 288;" ::: "memory");   // local rows + zero-fill complete (warp 2's acks wait for this)
@@ -1020,7 +1030,7 @@ __device__ __forceinline__ void dispatch_phase(const FmParams& p, uint8_t* smem,
         fence_proxy_async_all();   // ... and are ordered before the generic-proxy acknowledgements
     }
     __syncwarp();
-    // the remote acknowledgements also tell the peers that this chunk's output rows are zeroed (TMA stores issued by warp 4
+    // the remote acknowledgements also tell the peers that this chunk's output rows are zeroed (TMA stores issued by warp 11
     // in the router, completed before it arrives here) and that the routing records are written
     asm volatile("bar.sync 6, 288;" ::: "memory");
     if (in_regs) {
@@ -1226,7 +1236,7 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
     const TileInfo* ring = reinterpret_cast<const TileInfo*>(smem + OFF_RING);
     const int lane = threadIdx.x & 31;
     int stage = 0, phase = 0, q = 0, qphase = 0;
-    bool first = true;
+    bool first = true, stamped = false;
     for (;;) {
         int kind = -1, gather = 0, g_base = 0, g_rows = 0;
         TileInfo ti;
@@ -1308,6 +1318,7 @@ __device__ __forceinline__ void ffn_producer(const FmParams& p, uint8_t* smem, u
                     if (ld_a && !gather) tma_load_2d(sa, ta, kb * BLOCK_K, a_row, &full[stage]);
                     if (ld_b) tma_load_2d(sa + A_STAGE_BYTES, tb, kb * BLOCK_K, b_row, &full[stage]);
                 }
+                if (!stamped) { trace_stamp(p, 7); stamped = true; }   // first loads of the first tile issued
             }
             if (gather) {   // warp-uniform
                 __syncwarp();   // lane 0 has seen the stage empty

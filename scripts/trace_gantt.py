@@ -22,7 +22,7 @@ def analyse(tr, cfg, label=""):
     t00 = tr[:, 0].min()
     us = lambda a: (a - t00) / 1e3  # noqa: E731
     names = {0: "start", 11: "gate_gemv", 10: "zero_issued", 15: "topk_warp0", 12: "gate_topk", 1: "gate_done", 2: "barrier", 8: "disp_prefix", 9: "disp_rows_done",
-             3: "dispatch_end", 4: "ffn_start", 5: "ffn_end", 6: "kernel_end"}
+             3: "dispatch_end", 7: "first_tma_issued", 4: "ffn_start", 5: "ffn_end", 6: "kernel_end"}
     print(f"--- {label} phases (us after the first CTA's start; min / median / max over CTAs)")
     for i, nm in names.items():
         v = us(tr[:, i][tr[:, i] > 0])
