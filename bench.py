@@ -307,18 +307,38 @@ def parity_check(env, ctx, cfg, xd, wgd, wed, n_tokens):
     rng = np.random.default_rng(1234 + env.rank)
     sample = np.sort(rng.choice(cfg.S, size=min(n_tokens, cfg.S), replace=False)).astype(np.int32)
     xb = mo.to_bits(xd.cpu().reshape(cfg.S, cfg.H))
-    ref = mo.forward_sample(xb, mo.gate_weights_effective(mo.to_bits(wgd.cpu()), cfg.E, cfg.H), up, down, sample,
-                            k=cfg.k, EC=cfg.EC, act=cfg.hidden_act)
+    wg_eff = mo.gate_weights_effective(mo.to_bits(wgd.cpu()), cfg.E, cfg.H)
+    ref = mo.forward_sample(xb, wg_eff, up, down, sample, k=cfg.k, EC=cfg.EC, act=cfg.hidden_act)
     mism = (topk != ref.topk_idx).any(axis=1)
     hard = int((mism & ~ref.ambiguous).sum())
     got = mo.bits_to_f32(mo.to_bits(out.cpu().reshape(cfg.S, cfg.H))[sample]).astype(np.float64)
-    want = mo.bits_to_f32(ref.out).astype(np.float64)
     ok_rows = ~mism[sample]
     finite = bool(np.isfinite(got).all())
-    relf = float(np.linalg.norm(got[ok_rows] - want[ok_rows]) / max(np.linalg.norm(want[ok_rows]), 1e-30)) if finite else float("inf")
-    ok = finite and hard == 0 and relf <= 1e-3
-    res = torch.tensor([relf if finite else 1e30, float(hard), float(int(mism.sum())), 0.0 if ok else 1.0],
-                       dtype=torch.float64, device=env.dev)
+
+    def rel_frobenius(want_bits):
+        want = mo.bits_to_f32(want_bits).astype(np.float64)
+        if not finite:
+            return float("inf")
+        return float(np.linalg.norm(got[ok_rows] - want[ok_rows]) / max(np.linalg.norm(want[ok_rows]), 1e-30))
+
+    relf_plain = rel_frobenius(ref.out)
+    # Router weights: the bf16 rounding of a gate probability hangs on the last bits of its fp32 logit, i.e. on the
+    # summation order of the router GEMM (sequential in the oracle, tensor-core tiles on the device from 17 experts, as in
+    # the reference).  They must agree to <= 1 bf16 ulp; where some differ, the FFN + combine arithmetic is judged with
+    # the oracle evaluated on the DEVICE's router weights, and the plain end-to-end figure is reported next to it.
+    dev_w = np.ascontiguousarray(ctx.read("topk_w")).view(np.uint16).reshape(cfg.S, cfg.k)[sample]
+    dev_mcw = np.ascontiguousarray(ctx.read("mcw"), dtype=np.float32).reshape(cfg.S)[sample]
+    ulps = mo.router_weight_ulps(dev_w, ref, sample)[ok_rows]
+    flips = int((ulps > 0).sum())
+    max_ulp = int(ulps.max()) if ulps.size else 0
+    relf = relf_plain
+    if flips and finite:
+        ref_w = mo.forward_sample(xb, wg_eff, up, down, sample, k=cfg.k, EC=cfg.EC, act=cfg.hidden_act,
+                                  topk_w_given=dev_w, mcw_given=dev_mcw)
+        relf = rel_frobenius(ref_w.out)
+    ok = finite and hard == 0 and max_ulp <= 1 and relf <= 1e-3
+    res = torch.tensor([relf if finite else 1e30, float(hard), float(int(mism.sum())), 0.0 if ok else 1.0,
+                        relf_plain if finite else 1e30, float(flips), float(max_ulp)], dtype=torch.float64, device=env.dev)
     if env.world > 1:
         allr = [torch.empty_like(res) for _ in range(env.world)]
         dist.all_gather(allr, res)
@@ -328,6 +348,11 @@ def parity_check(env, ctx, cfg, xd, wgd, wed, n_tokens):
     return {"n_ranks": env.world, "tokens_checked": int(len(sample)) * env.world, "tokens_routed_per_rank": cfg.S,
             "relF_max": float(allr[:, 0].max()), "topk_mismatch_unambiguous": int(allr[:, 1].sum()),
             "topk_mismatch_ambiguous": int(allr[:, 2].sum() - allr[:, 1].sum()), "tolerance_relF": 1e-3,
+            "router_weights_off_by_one_bf16_ulp": int(allr[:, 5].sum()), "router_weight_max_ulp": int(allr[:, 6].max()),
+            "relF_max_with_oracle_router_weights": float(allr[:, 4].max()),
+            "rule": "top-k indices exact on unambiguous tokens; router weights within 1 bf16 ulp of the oracle's; "
+                    "relF <= tolerance against the oracle's FFN + combine on the device's router weights (the plain "
+                    "end-to-end relF, which includes the 0.4 % steps of those ulps, is reported next to it)",
             "inputs": "x N(0,1), gate/expert weights N(0,1)*d_model^-0.5, seeded; checked against oracle/moe_oracle.c",
             "ok": bool(allr[:, 3].sum() == 0)}
 

@@ -392,12 +392,19 @@ done:
  * cost of the FFN is per row, so full-size shapes (d_model 4096, ffn 14336) stay at seconds.  out_sample [n_sample,H].
  * Used by bench.py's post-run parity check and the full-size multi-GPU parity runs.
  */
-FMO_API int fmo_forward_sample(const uint16_t* x, const uint16_t* wg_eff, const uint16_t* w_up,
-                               const uint16_t* w_down_eff, const uint16_t* b_up, const uint16_t* b_down, int S, int H,
-                               int P, int E, int k, int EC, int act, const int32_t* sample, int n_sample,
-                               uint16_t* out_sample, int32_t* topk_idx_out, int32_t* slot_out, int32_t* kept_out,
-                               int32_t* counts_out, float* mcw_out, uint16_t* gate_out_out, float* logits_out,
-                               float* abs_sum_out) {
+/* Variant used by the parity checks: `topk_w_given` [n_sample,k] (bf16 bits) / `mcw_given` [n_sample], when not NULL,
+ * replace the oracle's own combine weights of the sampled tokens (gateOut[t, e_j] and the top-k probability sum).  The
+ * bf16 rounding of a gate probability is decided by the last bits of its fp32 logit, i.e. by the summation order of
+ * the router GEMM (sequential here, tensor-core tiles on the device and in the reference): a device weight may sit
+ * one bf16 ulp (0.4 %) from the oracle's.  Feeding the device's weights separates that from the expert FFN + combine
+ * arithmetic, which is then held to the usual tolerance; the weights themselves are held to <= 1 ulp by the caller. */
+FMO_API int fmo_forward_sample_w(const uint16_t* x, const uint16_t* wg_eff, const uint16_t* w_up,
+                                 const uint16_t* w_down_eff, const uint16_t* b_up, const uint16_t* b_down, int S, int H,
+                                 int P, int E, int k, int EC, int act, const int32_t* sample, int n_sample,
+                                 const uint16_t* topk_w_given, const float* mcw_given,
+                                 uint16_t* out_sample, int32_t* topk_idx_out, int32_t* slot_out, int32_t* kept_out,
+                                 int32_t* counts_out, float* mcw_out, uint16_t* gate_out_out, float* logits_out,
+                                 float* abs_sum_out) {
     const size_t SE = (size_t)S * E;
     float* probs = (float*)malloc(sizeof(float) * SE);
     int rc = -2;
@@ -454,14 +461,25 @@ FMO_API int fmo_forward_sample(const uint16_t* x, const uint16_t* wg_eff, const 
         for (int j = 0; j < k; ++j) {
             const int e = topk_idx_out[(size_t)t * k + j];
             yr[j] = rowpos[(size_t)i * k + j] >= 0 ? ybuf + (size_t)rowpos[(size_t)i * k + j] * H : NULL;
-            pt[j] = gate_out_out[(size_t)t * E + e];
+            pt[j] = topk_w_given ? topk_w_given[(size_t)i * k + j] : gate_out_out[(size_t)t * E + e];
         }
-        fmo_combine_token(yr, pt, mcw_out[t], k, H, out_sample + (size_t)i * H);
+        fmo_combine_token(yr, pt, mcw_given ? mcw_given[i] : mcw_out[t], k, H, out_sample + (size_t)i * H);
     }
     rc = 0;
 done:
     free(rows); free(hbuf); free(ybuf); free(yoff); free(fill); free(rowpos); free(probs);
     return rc;
+}
+
+FMO_API int fmo_forward_sample(const uint16_t* x, const uint16_t* wg_eff, const uint16_t* w_up,
+                               const uint16_t* w_down_eff, const uint16_t* b_up, const uint16_t* b_down, int S, int H,
+                               int P, int E, int k, int EC, int act, const int32_t* sample, int n_sample,
+                               uint16_t* out_sample, int32_t* topk_idx_out, int32_t* slot_out, int32_t* kept_out,
+                               int32_t* counts_out, float* mcw_out, uint16_t* gate_out_out, float* logits_out,
+                               float* abs_sum_out) {
+    return fmo_forward_sample_w(x, wg_eff, w_up, w_down_eff, b_up, b_down, S, H, P, E, k, EC, act, sample, n_sample, NULL,
+                                NULL, out_sample, topk_idx_out, slot_out, kept_out, counts_out, mcw_out, gate_out_out,
+                                logits_out, abs_sum_out);
 }
 
 /* ------------------------------------------------------------------ training-mode auxiliary (load-balancing) loss

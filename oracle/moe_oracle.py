@@ -44,6 +44,7 @@ def lib() -> ctypes.CDLL:
         L.fmo_expert_ffn.restype = ctypes.c_int
         L.fmo_forward.restype = ctypes.c_int
         L.fmo_forward_sample.restype = ctypes.c_int
+        L.fmo_forward_sample_w.restype = ctypes.c_int
         L.fmo_num_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -175,10 +176,15 @@ def forward(x: np.ndarray, wg_eff: np.ndarray, w_up: np.ndarray, w_down_eff: np.
 
 def forward_sample(x: np.ndarray, wg_eff: np.ndarray, w_up: np.ndarray, w_down_eff: np.ndarray, sample: np.ndarray, *,
                    k: int, EC: int, act: int = 0, b_up: Optional[np.ndarray] = None,
-                   b_down: Optional[np.ndarray] = None) -> OracleResult:
+                   b_down: Optional[np.ndarray] = None, topk_w_given: Optional[np.ndarray] = None,
+                   mcw_given: Optional[np.ndarray] = None) -> OracleResult:
     """Like `forward`, but the expert FFN + combine run only for the tokens listed in `sample` (routing, slots and
     capacity drops are still computed over all S tokens).  `out` of the result is [len(sample), H] in sample order;
-    every other field covers all S tokens.  Keeps full-size shapes (d_model 4096, ffn 14336) at seconds of CPU."""
+    every other field covers all S tokens.  Keeps full-size shapes (d_model 4096, ffn 14336) at seconds of CPU.
+
+    `topk_w_given` (bf16 bits [len(sample), k]) / `mcw_given` (float32 [len(sample)]): combine with these router weights
+    instead of the oracle's own (see fmo_forward_sample_w: separates 1-ulp differences of the bf16 gate probabilities,
+    which depend on the router GEMM's summation order, from the FFN + combine arithmetic)."""
     S, H = x.shape
     E, P, H2 = w_up.shape
     assert H2 == H and wg_eff.shape == (E, H) and w_down_eff.shape == (E, H, P)
@@ -193,17 +199,29 @@ def forward_sample(x: np.ndarray, wg_eff: np.ndarray, w_up: np.ndarray, w_down_e
     gate_out = np.zeros((S, E), dtype=np.uint16)
     logits = np.zeros((S, E), dtype=np.float32)
     abs_sum = np.zeros((S,), dtype=np.float32)
-    rc = lib().fmo_forward_sample(
+    wv = None if topk_w_given is None else np.ascontiguousarray(topk_w_given, dtype=np.uint16).reshape(n, k)
+    mv = None if mcw_given is None else np.ascontiguousarray(mcw_given, dtype=np.float32).reshape(n)
+    rc = lib().fmo_forward_sample_w(
         _p(np.ascontiguousarray(x), _u16p), _p(np.ascontiguousarray(wg_eff), _u16p),
         _p(np.ascontiguousarray(w_up), _u16p), _p(np.ascontiguousarray(w_down_eff), _u16p),
         _p(None if b_up is None else np.ascontiguousarray(b_up), _u16p),
         _p(None if b_down is None else np.ascontiguousarray(b_down), _u16p),
         ctypes.c_int(S), ctypes.c_int(H), ctypes.c_int(P), ctypes.c_int(E), ctypes.c_int(k), ctypes.c_int(EC),
-        ctypes.c_int(act), _p(sample, _i32p), ctypes.c_int(n), _p(out, _u16p), _p(topk, _i32p), _p(slot, _i32p),
+        ctypes.c_int(act), _p(sample, _i32p), ctypes.c_int(n), _p(wv, _u16p), _p(mv, _f32p), _p(out, _u16p),
+        _p(topk, _i32p), _p(slot, _i32p),
         _p(kept, _i32p), _p(counts, _i32p), _p(mcw, _f32p), _p(gate_out, _u16p), _p(logits, _f32p), _p(abs_sum, _f32p))
     if rc != 0:
-        raise RuntimeError(f"fmo_forward_sample failed with code {rc}")
+        raise RuntimeError(f"fmo_forward_sample_w failed with code {rc}")
     return OracleResult(out, topk, slot, kept, counts, mcw, gate_out, logits, ambiguity_flags(logits, abs_sum, k))
+
+
+def router_weight_ulps(dev_topk_w: np.ndarray, ref: OracleResult, sample: np.ndarray) -> np.ndarray:
+    """Distance in bf16 ulps between the device's top-k router weights (bf16 bits [len(sample), k]) and the oracle's
+    gateOut[t, e_j] for the sampled tokens (meaningful where the top-k indices agree; probabilities are positive, so the
+    ulp distance is the difference of the bit patterns)."""
+    t = np.asarray(sample, dtype=np.int64)
+    ref_w = ref.gate_out[t[:, None], ref.topk_idx[t]]
+    return np.abs(np.asarray(dev_topk_w, dtype=np.uint16).astype(np.int64) - ref_w.astype(np.int64))
 
 
 def aux_loss(x: np.ndarray, wg_eff: np.ndarray, *, k: int, EC: int):

@@ -57,3 +57,77 @@ def test_usable_cpus_respects_affinity():
 
     n = bench.usable_cpus()
     assert 1 <= n <= (os.cpu_count() or 1)
+
+
+class _FakeEnv:
+    world, rank = 1, 0
+
+    def __init__(self):
+        import torch
+
+        self.dev = torch.device("cpu")
+
+
+class _OracleBackedContext:
+    """Stands in for MoEContext in bench.parity_check: `forward` is the oracle itself, optionally with some router weights
+    moved by `ulp` bf16 ulps (and the output recomputed with them), the way a different summation order of the router GEMM
+    would."""
+
+    def __init__(self, cfg, flip_tokens=(), ulp=1):
+        self.cfg, self.flip_tokens, self.ulp, self.bufs = cfg, list(flip_tokens), ulp, {}
+
+    def forward(self, xd, wgd, wed):
+        import numpy as np
+        import torch
+
+        from oracle import moe_oracle as mo
+
+        cfg = self.cfg
+        xb = mo.to_bits(xd.reshape(cfg.S, cfg.H))
+        wg_eff = mo.gate_weights_effective(mo.to_bits(wgd), cfg.E, cfg.H)
+        up, down = mo.split_expert_weights(mo.to_bits(wed))
+        ref = mo.forward(xb, wg_eff, up, down, k=cfg.k, EC=cfg.EC, act=cfg.hidden_act)
+        topk_w = ref.gate_out[np.arange(cfg.S)[:, None], ref.topk_idx].astype(np.uint16)
+        out = ref.out.copy()
+        if self.flip_tokens:
+            topk_w[self.flip_tokens, 0] += self.ulp
+            smp = np.asarray(sorted(self.flip_tokens), dtype=np.int32)
+            alt = mo.forward_sample(xb, wg_eff, up, down, smp, k=cfg.k, EC=cfg.EC, act=cfg.hidden_act,
+                                    topk_w_given=topk_w[smp], mcw_given=ref.mcw[smp])
+            out[smp] = alt.out
+        self.bufs = {"topk_idx": ref.topk_idx, "topk_w": topk_w, "mcw": ref.mcw}
+        return torch.from_numpy(out.view(np.int16)).view(torch.bfloat16).reshape(1, cfg.S, cfg.H)
+
+    def synchronize(self):
+        pass
+
+    def read(self, name):
+        return self.bufs[name]
+
+
+def _parity_case(flip_tokens, ulp):
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from flashmoe_b200.config import MoEConfig
+
+    cfg = MoEConfig(num_experts=8, expert_top_k=2, sequence_len=128, hidden_size=64, intermediate_size=128)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, cfg.S, cfg.H, generator=g).bfloat16()
+    wg = torch.randn(cfg.H, cfg.E, generator=g).bfloat16()
+    we = torch.randn(cfg.E, 2, cfg.P, cfg.H, generator=g).bfloat16()
+    ctx = _OracleBackedContext(cfg, flip_tokens, ulp)
+    return bench.parity_check(_FakeEnv(), ctx, cfg, x, wg, we, cfg.S)
+
+
+def test_parity_check_rule_on_router_weight_ulps():
+    """bench.parity_check: identical router weights -> plain comparison; weights one bf16 ulp off -> still ok, judged on
+    the device's weights, flips counted, plain relF reported next to it; two ulps off -> not ok."""
+    same = _parity_case([], 1)
+    assert same["ok"] and same["router_weights_off_by_one_bf16_ulp"] == 0 and same["relF_max"] == 0.0
+    one = _parity_case([5, 17, 99], 1)
+    assert one["ok"] and one["router_weights_off_by_one_bf16_ulp"] == 3 and one["router_weight_max_ulp"] == 1
+    assert one["relF_max"] == 0.0 and one["relF_max_with_oracle_router_weights"] > 0.0
+    two = _parity_case([5], 2)
+    assert not two["ok"] and two["router_weight_max_ulp"] == 2
