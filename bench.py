@@ -541,12 +541,13 @@ def main():
     sweeps = [s for s in args.sweeps.split(",") if s and s != "none"]
     if sweeps:
         line["sweeps"] = []
-        t_budget = time.perf_counter() + float(os.environ.get("FM_BENCH_SWEEP_BUDGET_S", "240"))
+        t_sweeps0, sweep_budget = time.perf_counter(), float(os.environ.get("FM_BENCH_SWEEP_BUDGET_S", "240"))
         for sname in sweeps:
             if sname not in BASELINE_CONFIGS or BASELINE_CONFIGS[sname].E % world:
                 line["sweeps"].append({"config": sname, "skipped": "num_experts not divisible by the world size"})
                 continue
-            if time.perf_counter() > t_budget:
+            # (a collective decision: ranks that disagreed about skipping would wait for each other forever)
+            if env.max_over_ranks(time.perf_counter() - t_sweeps0) > sweep_budget:
                 line["sweeps"].append({"config": sname, "skipped": "sweep time budget exhausted"})
                 continue
             try:
