@@ -236,7 +236,8 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
 struct GateTcState { int gkb; uint32_t accphase; };
 template <bool PAIR>
 __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem, int t0, int s0, int n_sub, int rows_span,
-                                               uint32_t crank, uint32_t tmem_base, float* logit_s, int ldl, GateTcState& st) {
+                                               int rows_cap, uint32_t crank, uint32_t tmem_base, float* logit_s, int ldl,
+                                               GateTcState& st) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BARS);
     uint64_t* gfull = bars + BAR_GFULL;
     uint64_t* gempty = bars + BAR_GEMPTY;
@@ -252,9 +253,13 @@ __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem,
                                                                  // accumulator rows are never read)
     const uint32_t tx_cta = (uint32_t)(a_bytes + b_bytes);
     // stages live in the router's weight + logits scratch (the logits are written only after the last MMA of the
-    // sub-chunk has completed); compact stride = what is staged, so a 28-token chunk with 8 experts gets 8 stages of 5 KB
-    const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
-    const int NS = max(1, min(GATE_STAGES, (G_WG_BYTES + G_LOGIT_BYTES - (A_STAGE_BYTES - a_bytes)) / stage_bytes));
+    // sub-chunk has completed); compact stride = what a FULL sub-chunk stages, so a 28-token chunk with 8 experts gets 8
+    // stages of 5 KB.  The layout (stride, stage count, offset of the Wg rows) is the same for every sub-chunk of the
+    // launch -- the stage / phase arithmetic runs across sub-chunks -- only the number of x boxes loaded follows rows_span
+    // (the last sub-chunk of a CTA is usually shorter).
+    const int a_cap = ((rows_cap + 31) / 32) * 32 * BLOCK_K * 2;
+    const int stage_bytes = (a_cap + b_bytes + 1023) & ~1023;
+    const int NS = max(1, min(GATE_STAGES, (G_WG_BYTES + G_LOGIT_BYTES - (A_STAGE_BYTES - a_cap)) / stage_bytes));
     if (warp == 0 && lane == 0) {          // TMA issuer of this CTA
         for (int kb = 0; kb < nk; ++kb) {
             const int g = st.gkb + kb, s = g % NS;
@@ -266,11 +271,11 @@ __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem,
                 const uint32_t leader_full = mapa_shared(smem_u32(&gfull[s]), 0);
                 for (int j = 0; j < nb32; ++j)
                     tma_load_2d_pair(sa + j * 4096, &p.tm_gx, kb * BLOCK_K, t0 + s0 + j * 32, leader_full);
-                tma_load_2d_pair(sa + a_bytes, &p.tm_gw, kb * BLOCK_K, (int)crank * b_rows, leader_full);
+                tma_load_2d_pair(sa + a_cap, &p.tm_gw, kb * BLOCK_K, (int)crank * b_rows, leader_full);
             } else {
                 mbar_arrive_expect_tx(&gfull[s], tx_cta);
                 for (int j = 0; j < nb32; ++j) tma_load_2d(sa + j * 4096, &p.tm_gx, kb * BLOCK_K, t0 + s0 + j * 32, &gfull[s]);
-                tma_load_2d(sa + a_bytes, &p.tm_gw, kb * BLOCK_K, 0, &gfull[s]);
+                tma_load_2d(sa + a_cap, &p.tm_gw, kb * BLOCK_K, 0, &gfull[s]);
             }
         }
     } else if (warp == 1 && lane == 0 && crank == 0) {   // MMA issuer (leader CTA)
@@ -282,7 +287,7 @@ __device__ __forceinline__ void gate_logits_tc(const FmParams& p, uint8_t* smem,
             tcgen05_fence_after();
             const uint32_t sa = smem_u32(smem + G_OFF_WG + s * stage_bytes);
             const uint64_t da = umma_smem_desc_sw128(sa);
-            const uint64_t db = umma_smem_desc_sw128(sa + a_bytes);
+            const uint64_t db = umma_smem_desc_sw128(sa + a_cap);
 #pragma unroll
             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                 if (PAIR) umma_bf16_ss_pair(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (kb | kk) != 0 ? 1u : 0u);
@@ -381,7 +386,7 @@ __device__ __forceinline__ void gate_phase(const FmParams& p, uint8_t* smem, int
                 if (PAIR) cluster_sync_all(); else __syncthreads();
                 tcgen05_fence_after();
             }
-            gate_logits_tc<PAIR>(p, smem, t0, s0, n_sub, min(TS, p.tpc - s0), crank, tmem_base, logit_s, ldl, tcs);
+            gate_logits_tc<PAIR>(p, smem, t0, s0, n_sub, min(TS, p.tpc - s0), min(TS, p.tpc), crank, tmem_base, logit_s, ldl, tcs);
         } else {
         for (int i = tid; i < n_sub * ldl; i += NUM_THREADS) logit_s[i] = 0.0f;
         for (int eg0 = 0; eg0 < E; eg0 += EG) {

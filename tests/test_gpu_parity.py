@@ -71,6 +71,12 @@ CASES = {
     "E32_k2": MoEConfig(num_experts=32, expert_top_k=2, sequence_len=1024, hidden_size=512, intermediate_size=512),
     "E64_k4": MoEConfig(num_experts=64, expert_top_k=4, sequence_len=512, hidden_size=256, intermediate_size=256),
     "E128_k2": MoEConfig(num_experts=128, expert_top_k=2, sequence_len=1024, hidden_size=256, intermediate_size=256),
+    # 139 tokens per CTA: the tensor-core router walks two sub-chunks (128 + 11 tokens) with different numbers of x boxes
+    # (the 64k-token sweep point has four; a stage layout that followed the sub-chunk's row count broke its last one)
+    "E32_router_subchunks": MoEConfig(num_experts=32, expert_top_k=2, sequence_len=20480, hidden_size=128,
+                                      intermediate_size=128),
+    "E64_router_subchunks": MoEConfig(num_experts=64, expert_top_k=2, sequence_len=40960, hidden_size=128,
+                                      intermediate_size=64),
     "E1_dense": MoEConfig(num_experts=1, expert_top_k=1, sequence_len=256, hidden_size=128, intermediate_size=512),
     "k8": MoEConfig(num_experts=16, expert_top_k=8, sequence_len=256, hidden_size=128, intermediate_size=256),
     "multi_seq": MoEConfig(num_experts=8, expert_top_k=2, sequence_len=256, mini_batch=3, hidden_size=128,
