@@ -131,3 +131,25 @@ def test_parity_check_rule_on_router_weight_ulps():
     assert one["relF_max"] == 0.0 and one["relF_max_with_oracle_router_weights"] > 0.0
     two = _parity_case([5], 2)
     assert not two["ok"] and two["router_weight_max_ulp"] == 2
+
+
+def test_roofline_block_arithmetic():
+    """bench.derived: achieved = algorithmic FLOPs per launch / step time; burst peak for timed regions under a second,
+    sustained above; the NVLink figure is zero on one GPU."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    cfg = bench.BASELINE_CONFIGS["B"]
+    peaks = {"bf16_burst": 1696.0, "bf16_sustained": 1429.2, "hbm_gbs": 6584.5, "source": "test"}
+    res = {"cfg": cfg, "ms": 0.14, "rows_total": 8192, "nlx": 8}
+    r = bench.derived(res, 1, peaks, 200)
+    flops = 4.0 * 8192 * cfg.H * cfg.P + 2.0 * cfg.S * cfg.H * cfg.E
+    assert abs(r["algorithmic_flops_per_launch"] - flops) < 1
+    assert abs(r["achieved"] - flops / 0.14e-3 / 1e12) < 1e-6
+    assert r["peak"] == 1696.0 and abs(r["frac"] - r["achieved"] / 1696.0) < 1e-12 and "burst" in r["peak_kind"]
+    assert r["nvlink_bytes_per_dir_per_gpu"] == 0.0
+    long = bench.derived(res, 1, peaks, 20000)   # 2.8 s of timed region
+    assert long["peak"] == 1429.2 and "sustained" in long["peak_kind"]
+    r8 = bench.derived({"cfg": cfg, "ms": 0.18, "rows_total": 8 * 8192, "nlx": 1}, 8, peaks, 20)
+    assert abs(r8["nvlink_bytes_per_dir_per_gpu"] - 2.0 * 8192 * (7 / 8) * cfg.H * 2) < 1
+    assert abs(r8["algorithmic_flops_per_launch"] - flops) < 1   # weak scaling: per-GPU work fixed
